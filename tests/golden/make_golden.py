@@ -1,0 +1,194 @@
+"""Generate the golden fixtures in this directory by EXECUTING REFERENCE CODE.
+
+Runs only in the build container (needs /root/reference, which does not exist on the GPU box);
+the outputs (*.npz) are committed so tests never read the reference at run time.
+
+What is executed:
+  * parler_tts.modeling_parler_tts.build_delay_pattern_mask / apply_delay_pattern_mask  (verbatim)
+  * parler_tts.logits_processors.ParlerTTSLogitsProcessor                               (verbatim, shim: isin)
+  * parler_tts.ParlerTTSForCausalLM.forward(use_cache=False) with sdpa attention        (verbatim, 3 import shims)
+  * transformers.models.dac.DacModel.decode  -- stand-in for descript-audio-codec (not installed)
+Import shims: stub `dac.model.DAC`; `cache_utils.SlidingWindowCache`;
+`pytorch_utils.isin_mps_friendly = torch.isin`.
+
+Usage:  python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+
+def import_reference():
+    import transformers.cache_utils as cu
+    import transformers.pytorch_utils as pu
+    if not hasattr(cu, "SlidingWindowCache"):
+        cu.SlidingWindowCache = cu.StaticCache
+    if not hasattr(pu, "isin_mps_friendly"):
+        pu.isin_mps_friendly = torch.isin
+    dac = types.ModuleType("dac")
+    dacm = types.ModuleType("dac.model")
+
+    class DAC(torch.nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+    dacm.DAC = DAC
+    dac.model = dacm
+    sys.modules["dac"], sys.modules["dac.model"] = dac, dacm
+    sys.path.insert(0, "/root/reference")
+    import parler_tts
+    return parler_tts
+
+
+def gen_delay(pt):
+    from parler_tts.modeling_parler_tts import build_delay_pattern_mask, apply_delay_pattern_mask
+    out = {}
+    cases = [(2, 4, 1, 8), (1, 9, 1, 257), (3, 9, 1, 20), (2, 4, 3, 12), (1, 9, 1, 16), (2, 9, 1, 17), (1, 4, 1, 6)]
+    g = torch.Generator().manual_seed(5)
+    for ci, (B, K, seq, L) in enumerate(cases):
+        ids = torch.randint(0, 60, (B * K, seq), generator=g)
+        ids[:, 0] = 65
+        d, m = build_delay_pattern_mask(ids, 65, 64, L, K)
+        full = torch.randint(0, 60, (B * K, L), generator=g)
+        app = apply_delay_pattern_mask(full, m)
+        part = apply_delay_pattern_mask(full[:, : max(1, L // 2)], m)
+        out[f"c{ci}_meta"] = np.array([B, K, seq, L])
+        out[f"c{ci}_ids"] = ids.numpy()
+        out[f"c{ci}_delayed"] = d.numpy()
+        out[f"c{ci}_mask"] = m.numpy()
+        out[f"c{ci}_full"] = full.numpy()
+        out[f"c{ci}_applied"] = app.numpy()
+        out[f"c{ci}_applied_half"] = part.numpy()
+    out["n"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(HERE, "delay_pattern.npz"), **out)
+
+
+def gen_logits_processor(pt):
+    from parler_tts.logits_processors import ParlerTTSLogitsProcessor
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    B, K, V, eos, steps = 3, 4, 96, 64, 14
+    proc = ParlerTTSLogitsProcessor(eos, K, B, "cpu")
+    ids = torch.full((B * K, 1), 65, dtype=torch.long)
+    hist_scores_in, hist_scores_out, hist_first = [], [], []
+    for s in range(steps):
+        scores = torch.randn(B * K, V, generator=g)
+        hist_scores_in.append(scores.numpy().copy())
+        o = proc(ids, scores.clone())
+        hist_scores_out.append(o.numpy().copy())
+        hist_first.append(proc.first_codebooks_unfinished.numpy().copy())
+        nxt = torch.randint(0, 60, (B * K,), generator=g)
+        # scripted EOS events: codebook 0 of sample 0 at step 2, then cascading; sample 2 cb0 at step 5
+        if s == 2:
+            nxt[0] = eos
+        if s >= 3:
+            nxt[0] = eos  # finished row keeps emitting pad == eos (Q11)
+        if s == 4:
+            nxt[1] = eos
+        if s == 5:
+            nxt[8] = eos
+        if s == 6:
+            nxt[2] = eos
+            nxt[5] = eos  # a non-first codebook of sample 1 (cannot advance sample 1)
+        ids = torch.cat([ids, nxt[:, None]], dim=1)
+    out.update(meta=np.array([B, K, V, eos, steps]), ids=ids.numpy(), scores_in=np.stack(hist_scores_in),
+               scores_out=np.stack(hist_scores_out), first=np.stack(hist_first))
+    np.savez_compressed(os.path.join(HERE, "logits_processor.npz"), **out)
+
+
+def gen_decoder(pt):
+    from parler_tts import ParlerTTSDecoderConfig, ParlerTTSForCausalLM
+    from oracle.config import tiny_cfg
+    from oracle.weights import make_decoder_weights
+    out = {}
+    for name, kw in (("abs", dict(rope_embeddings=False)), ("rope", dict(rope_embeddings=True)),
+                     ("gqa", dict(rope_embeddings=True, num_attention_heads=4, num_key_value_heads=2,
+                                  num_cross_attention_key_value_heads=1, hidden_size=256))):
+        cfg = tiny_cfg(**kw)
+        w = make_decoder_weights(cfg, seed=3)
+        rc = ParlerTTSDecoderConfig(
+            vocab_size=cfg.vocab_size, max_position_embeddings=cfg.max_position_embeddings,
+            num_hidden_layers=cfg.num_hidden_layers, ffn_dim=cfg.ffn_dim, num_attention_heads=cfg.num_attention_heads,
+            num_key_value_heads=cfg.num_key_value_heads,
+            num_cross_attention_key_value_heads=cfg.num_cross_attention_key_value_heads,
+            hidden_size=cfg.hidden_size, num_codebooks=cfg.num_codebooks, pad_token_id=cfg.pad_token_id,
+            eos_token_id=cfg.eos_token_id, bos_token_id=cfg.bos_token_id, dropout=0.0,
+            rope_embeddings=cfg.rope_embeddings, activation_function=cfg.activation_function)
+        rc._attn_implementation = "sdpa"
+        m = ParlerTTSForCausalLM(rc).eval()
+        sd = {k[len("decoder."):]: v for k, v in w.items() if k.startswith("decoder.")}
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected, unexpected
+        assert all("embed_positions" in k or "rotary" in k for k in missing), missing
+        g = torch.Generator().manual_seed(7)
+        B, K, T, P, S = 2, cfg.num_codebooks, 6, 5, 7
+        ids = torch.randint(0, cfg.codebook_size, (B * K, T), generator=g)
+        ids[:, 0] = cfg.bos_token_id
+        enc = torch.randn(B, S, cfg.hidden_size, generator=g)
+        enc_mask = torch.ones(B, S, dtype=torch.long)
+        enc_mask[1, :3] = 0  # left padding on sample 1
+        enc = enc * enc_mask[..., None]
+        prompt = torch.randn(B, P, cfg.hidden_size, generator=g)
+        pmask = torch.ones(B, P, dtype=torch.long)
+        pmask[0, :2] = 0
+        with torch.no_grad():
+            lo = m(input_ids=ids, encoder_hidden_states=enc, encoder_attention_mask=enc_mask,
+                   prompt_hidden_states=prompt, prompt_attention_mask=pmask, use_cache=False).logits
+            lo_nomask = m(input_ids=ids, encoder_hidden_states=enc, prompt_hidden_states=prompt, use_cache=False).logits
+        out[f"{name}_ids"] = ids.numpy()
+        out[f"{name}_enc"] = enc.numpy()
+        out[f"{name}_enc_mask"] = enc_mask.numpy()
+        out[f"{name}_prompt"] = prompt.numpy()
+        out[f"{name}_pmask"] = pmask.numpy()
+        out[f"{name}_logits"] = lo.numpy()  # [B*K, P+T, V]
+        out[f"{name}_logits_nomask"] = lo_nomask.numpy()
+    np.savez_compressed(os.path.join(HERE, "decoder_forward.npz"), **out)
+
+
+def gen_dac():
+    from transformers.models.dac import DacConfig, DacModel
+    from oracle.config import tiny_dac_cfg
+    from oracle.weights import make_dac_weights
+    cfg = tiny_dac_cfg()
+    hc = DacConfig(encoder_hidden_size=8, downsampling_ratios=[2, 4, 8, 8], decoder_hidden_size=cfg.decoder_hidden_size,
+                   n_codebooks=cfg.n_codebooks, codebook_size=cfg.codebook_size, codebook_dim=cfg.codebook_dim,
+                   hidden_size=cfg.hidden_size, upsampling_ratios=cfg.upsampling_ratios, sampling_rate=44100)
+    m = DacModel(hc).eval()
+    w = make_dac_weights(cfg, seed=2)
+    sd = m.state_dict()
+    loaded = 0
+    for k, v in w.items():
+        assert k in sd, k
+        assert sd[k].shape == v.shape, (k, sd[k].shape, v.shape)
+        sd[k] = v
+        loaded += 1
+    m.load_state_dict(sd)
+    dec_keys = [k for k in m.state_dict() if k.startswith("decoder.") or (k.startswith("quantizer.") and ("codebook" in k or "out_proj" in k))]
+    assert set(dec_keys) == set(w.keys()), set(dec_keys) ^ set(w.keys())
+    g = torch.Generator().manual_seed(4)
+    codes = torch.randint(0, cfg.codebook_size, (2, cfg.n_codebooks, 11), generator=g)
+    with torch.no_grad():
+        z = m.quantizer.from_codes(codes)[0]
+        audio = m.decode(audio_codes=codes).audio_values
+    np.savez_compressed(os.path.join(HERE, "dac_decode.npz"), codes=codes.numpy(), z=z.numpy(), audio=audio.numpy())
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    pt = import_reference()
+    gen_delay(pt)
+    gen_logits_processor(pt)
+    gen_decoder(pt)
+    gen_dac()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
