@@ -1,0 +1,500 @@
+// api.cu -- the C ABI (include/ptts_b200.h): argument validation, weight packing, the generation
+// session (prefill / decode step / sample / CUDA-graph replay) and DAC decode orchestration.
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "dac.h"
+#include "kernels.h"
+#include "layout.h"
+
+namespace ptts {
+static thread_local std::string g_err;
+void set_error(const std::string& m) { g_err = m; }
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+static bool env_flag(const char* name, bool dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return !(v[0] == '0' || v[0] == 'n' || v[0] == 'N' || v[0] == 'f' || v[0] == 'F');
+}
+}  // namespace ptts
+
+using namespace ptts;
+
+struct ptts_session {
+  ptts_decoder_config cfg;
+  DecoderLayout L;
+  WorkspaceLayout W;
+  const char* blob;
+  char* ws;
+  int sm_count;
+  bool pdl, use_graph;
+  bool has_prompt_mask, has_enc_mask, begun, prefilled;
+  ptts_gen_params gen;
+  cudaStream_t cap_stream;
+  cudaGraphExec_t exec;
+  bool graph_ready;
+  int64_t launches;  // kernels launched through this session (bench.py reports it)
+};
+
+extern "C" {
+
+const char* ptts_last_error(void) { return g_err.c_str(); }
+int ptts_version(void) { return 100; }
+
+// ---- weights ------------------------------------------------------------------------------------
+int ptts_decoder_blob_bytes(const ptts_decoder_config* cfg, int64_t* out_bytes) {
+  PTTS_REQUIRE(cfg && out_bytes, "null argument");
+  if (int e = validate_config(*cfg)) return e;
+  *out_bytes = make_layout(*cfg).total;
+  return PTTS_OK;
+}
+
+int ptts_decoder_pack(const ptts_decoder_config* cfg, void* blob, int32_t tensor_id, int32_t index, const void* src,
+                      int32_t src_dtype, int64_t rows, int64_t cols, void* stream) {
+  PTTS_REQUIRE(cfg && blob && src, "null argument");
+  if (int e = validate_config(*cfg)) return e;
+  PTTS_REQUIRE(src_dtype == PTTS_BF16 || src_dtype == PTTS_F32, "pack: src dtype must be bf16 or f32");
+  const DecoderLayout L = make_layout(*cfg);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = (char*)blob;
+  MatSlot ms;
+  const bool per_layer = (tensor_id >= PTTS_T_LN1_W && tensor_id <= PTTS_T_FC2);
+  if (per_layer) PTTS_REQUIRE(index >= 0 && index < L.L, "pack: layer %d out of range", index);
+  if (matrix_slot(L, tensor_id, index, &ms)) {
+    if (tensor_id == PTTS_T_LM_HEAD) PTTS_REQUIRE(index >= 0 && index < L.K, "pack: codebook %d out of range", index);
+    PTTS_REQUIRE(cols == ms.K, "pack: tensor %d expects %d columns, got %lld", tensor_id, ms.K, (long long)cols);
+    PTTS_REQUIRE(rows > 0 && ms.row_off + rows <= ms.N, "pack: tensor %d rows %lld do not fit fused matrix of %d rows", tensor_id, (long long)rows, ms.N);
+    return pack_matrix(src, src_dtype, rows, cols, ms.row_off, ms.K, base + ms.off, cfg->dtype, st);
+  }
+  const int64_t lb = L.layer0 + L.layer_stride * index;
+  const int H = L.H;
+  switch (tensor_id) {
+    case PTTS_T_EMBED_TOKENS:
+      PTTS_REQUIRE(index >= 0 && index < L.K && rows == L.V + 1 && cols == H, "pack: embed_tokens shape");
+      return pack_plain(src, src_dtype, rows * cols, base + L.embed + (int64_t)index * (L.V + 1) * H * L.es, cfg->dtype, st);
+    case PTTS_T_POS_TABLE:
+      PTTS_REQUIRE(!cfg->rope && rows == cfg->max_positions && cols == H, "pack: pos table shape");
+      return pack_plain(src, src_dtype, rows * cols, base + L.pos, cfg->dtype, st);
+    case PTTS_T_ROPE_COS:
+    case PTTS_T_ROPE_SIN:
+      PTTS_REQUIRE(cfg->rope && rows == cfg->max_positions && cols == PTTS_HEAD_DIM, "pack: rope table shape");
+      return pack_plain(src, src_dtype, rows * cols, base + (tensor_id == PTTS_T_ROPE_COS ? L.rope_cos : L.rope_sin), cfg->dtype, st);
+    case PTTS_T_LN1_W: case PTTS_T_LN1_B: case PTTS_T_LN2_W: case PTTS_T_LN2_B: case PTTS_T_LN3_W: case PTTS_T_LN3_B: {
+      PTTS_REQUIRE(rows * cols == H, "pack: LayerNorm parameter must have %d elements", H);
+      const int64_t off[6] = {L.ln1_w, L.ln1_b, 0, 0, 0, 0};
+      (void)off;
+      int64_t o = 0;
+      switch (tensor_id) {
+        case PTTS_T_LN1_W: o = L.ln1_w; break; case PTTS_T_LN1_B: o = L.ln1_b; break;
+        case PTTS_T_LN2_W: o = L.ln2_w; break; case PTTS_T_LN2_B: o = L.ln2_b; break;
+        case PTTS_T_LN3_W: o = L.ln3_w; break; default: o = L.ln3_b; break;
+      }
+      return pack_plain(src, src_dtype, H, base + lb + o, PTTS_F32, st);
+    }
+    case PTTS_T_FINAL_LN_W:
+    case PTTS_T_FINAL_LN_B:
+      PTTS_REQUIRE(rows * cols == H, "pack: LayerNorm parameter must have %d elements", H);
+      return pack_plain(src, src_dtype, H, base + (tensor_id == PTTS_T_FINAL_LN_W ? L.final_ln_w : L.final_ln_b), PTTS_F32, st);
+    default:
+      return fail(PTTS_EINVAL, "pack: unknown tensor id %d", tensor_id);
+  }
+}
+
+int ptts_workspace_bytes(const ptts_decoder_config* cfg, int32_t B, int32_t P, int32_t S, int32_t max_cache_len, int64_t* out_bytes) {
+  PTTS_REQUIRE(cfg && out_bytes, "null argument");
+  if (int e = validate_config(*cfg)) return e;
+  PTTS_REQUIRE(B > 0 && P >= 0 && S > 0 && max_cache_len > P, "workspace: need B>0, P>=0, S>0, max_cache_len>P (got %d %d %d %d)", B, P, S, max_cache_len);
+  PTTS_REQUIRE(max_cache_len <= cfg->max_positions || cfg->rope == 0 || true, "unreachable");
+  *out_bytes = make_workspace(*cfg, B, P, S, max_cache_len).total;
+  return PTTS_OK;
+}
+
+// ---- session ------------------------------------------------------------------------------------
+int ptts_session_create(const ptts_decoder_config* cfg, const void* blob, void* workspace, int64_t workspace_bytes,
+                        int32_t B, int32_t P, int32_t S, int32_t max_cache_len, ptts_session** out) {
+  PTTS_REQUIRE(cfg && blob && workspace && out, "null argument");
+  if (int e = validate_config(*cfg)) return e;
+  PTTS_REQUIRE(B > 0 && P >= 0 && S > 0 && max_cache_len > P, "session: bad shape B=%d P=%d S=%d Tmax=%d", B, P, S, max_cache_len);
+  PTTS_REQUIRE(max_cache_len <= cfg->max_positions, "session: cache length %d exceeds max_position_embeddings %d", max_cache_len, cfg->max_positions);
+  ptts_session* s = new (std::nothrow) ptts_session();
+  PTTS_REQUIRE(s, "out of host memory");
+  s->cfg = *cfg;
+  s->L = make_layout(*cfg);
+  s->W = make_workspace(*cfg, B, P, S, max_cache_len);
+  if (workspace_bytes < s->W.total) {
+    int64_t need = s->W.total;
+    delete s;
+    return fail(PTTS_EINVAL, "session: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes, (long long)need);
+  }
+  s->blob = (const char*)blob;
+  s->ws = (char*)workspace;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  s->sm_count = 148;
+  cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  s->pdl = env_flag("PTTS_PDL", true);
+  s->use_graph = env_flag("PTTS_GRAPH", true);
+  s->graph_ready = false;
+  s->exec = nullptr;
+  s->cap_stream = nullptr;
+  s->begun = s->prefilled = false;
+  s->launches = 0;
+  *out = s;
+  return PTTS_OK;
+}
+
+int ptts_session_destroy(ptts_session* s) {
+  if (!s) return PTTS_OK;
+  if (s->exec) cudaGraphExecDestroy(s->exec);
+  if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
+  delete s;
+  return PTTS_OK;
+}
+
+static SampleArgs sample_args(ptts_session* s) {
+  SampleArgs a{};
+  const WorkspaceLayout& W = s->W;
+  a.logits = (const float*)(s->ws + W.logits);
+  a.scores = (float*)(s->ws + W.scores);
+  a.raw_ids = (int64_t*)(s->ws + W.raw_ids);
+  a.raw_ld = W.raw_ld;
+  a.cur_ids = (int*)(s->ws + W.cur_ids);
+  a.eos_seen = (int*)(s->ws + W.eos_seen);
+  a.unfinished = (int*)(s->ws + W.unfinished);
+  a.first_unf = (int*)(s->ws + W.first_unf);
+  a.ctrl = (Ctrl*)(s->ws + W.ctrl);
+  a.gen = (const ptts_gen_params*)(s->ws + W.gen);
+  a.B = W.B; a.K = s->cfg.num_codebooks; a.V = s->cfg.vocab_size;
+  a.bos = s->cfg.bos_token_id; a.pad = s->cfg.pad_token_id; a.eos = s->cfg.eos_token_id;
+  return a;
+}
+
+int ptts_generate_begin(ptts_session* s, const ptts_gen_params* gen, void* stream) {
+  PTTS_REQUIRE(s && gen, "null argument");
+  PTTS_REQUIRE(gen->max_length >= 2, "generate: max_length must be >= 2, got %d", gen->max_length);
+  PTTS_REQUIRE(gen->max_length <= s->W.raw_ld, "generate: max_length %d exceeds the session's capacity %lld", gen->max_length, (long long)s->W.raw_ld);
+  PTTS_REQUIRE(!gen->do_sample || gen->temperature > 0.f, "`temperature` has to be a strictly positive float, got %f", gen->temperature);
+  PTTS_REQUIRE(gen->top_k >= 0, "`top_k` has to be a non-negative integer");
+  PTTS_REQUIRE(s->cfg.eos_token_id >= 0 && s->cfg.eos_token_id < s->cfg.vocab_size, "eos_token_id out of vocabulary");
+  cudaStream_t st = (cudaStream_t)stream;
+  s->gen = *gen;
+  PTTS_CHECK_CUDA(cudaMemcpyAsync(s->ws + s->W.gen, &s->gen, sizeof(ptts_gen_params), cudaMemcpyHostToDevice, st));
+  if (int e = launch_generate_begin(sample_args(s), st)) return e;
+  s->begun = true;
+  s->prefilled = false;
+  return PTTS_OK;
+}
+
+// one decoder pass over q_len new positions per batch row (q_len = P+1 at prefill, 1 at decode)
+static int run_forward(ptts_session* s, cudaStream_t st, bool prefill, const void* prompt_hidden, const void* enc_hidden) {
+  const ptts_decoder_config& c = s->cfg;
+  const DecoderLayout& L = s->L;
+  const WorkspaceLayout& W = s->W;
+  const int B = W.B, P = W.P, S = W.S, H = L.H, D = PTTS_HEAD_DIM;
+  const int q_len = prefill ? P + 1 : 1;
+  const int M = B * q_len;
+  const bool pdl = s->pdl && !prefill;  // the one-off prefill stays on plain stream order
+  const Ctrl* ctrl = prefill ? nullptr : (const Ctrl*)(s->ws + W.ctrl);
+  const int es = L.es;
+  char* ws = s->ws;
+  const char* blob = s->blob;
+
+  EmbedArgs ea{};
+  ea.tables = blob + L.embed;
+  ea.pos = c.rope ? nullptr : blob + L.pos;
+  ea.prefix = prefill ? prompt_hidden : nullptr;
+  ea.ids = (const int*)(ws + W.cur_ids);
+  ea.x = ws + W.x;
+  ea.ctrl = ctrl;
+  ea.B = B; ea.K = L.K; ea.V1 = L.V + 1; ea.H = H; ea.P = prefill ? P : 0;
+  ea.pos_from_ctrl = prefill ? 0 : 1; ea.pos0 = 0; ea.prefix_len = P;
+  if (int e = launch_embed(ea, c.dtype, st, pdl)) return e;
+  s->launches++;
+
+  auto lin = [&](const void* X, int64_t ldx, int64_t woff, int N, int K, const float* lw, const float* lb, int epi,
+                 const void* R, void* Y, int64_t ldy, int Mrows) -> int {
+    LinearArgs a{};
+    a.X = X; a.ldx = ldx; a.W = blob + woff; a.Y = Y; a.ldy = ldy; a.R = R; a.ldr = ldy;
+    a.ln_w = lw; a.ln_b = lb; a.eps = c.layer_norm_eps;
+    a.M = Mrows; a.N = N; a.K = K; a.Kc = (K > H && K % H == 0) ? H : K;
+    a.epi = epi; a.act = c.activation; a.ctrl = ctrl;
+    s->launches++;
+    return launch_linear(a, c.dtype, st, pdl, s->sm_count);
+  };
+
+  for (int i = 0; i < L.L; i++) {
+    const int64_t lb = L.layer0 + L.layer_stride * i;
+    char* x = ws + W.x;
+    if (prefill) {  // cross-attention K/V of the encoder states, once per generate() (:872-878)
+      if (int e = lin(enc_hidden, H, lb + L.wkvc, L.ckv_rows, H, nullptr, nullptr, EPI_STORE, nullptr,
+                      ws + W.cross_kv + W.cross_layer_stride * i, L.ckv_rows, B * S)) return e;
+    }
+    if (int e = lin(x, H, lb + L.wqkv, L.qkv_rows, H, (const float*)(blob + lb + L.ln1_w), (const float*)(blob + lb + L.ln1_b),
+                    EPI_STORE, nullptr, ws + W.qkv, L.qkv_rows, M)) return e;
+    AttnArgs at{};
+    at.q = ws + W.qkv; at.ldq = L.qkv_rows; at.q_col0 = 0;
+    at.knew = ws + W.qkv; at.vnew = ws + W.qkv; at.ldkv = L.qkv_rows; at.k_col0 = L.nh * D; at.v_col0 = (L.nh + L.nkv) * D;
+    char* kc = ws + W.self_kv + W.self_layer_stride * i;
+    at.kcache = kc; at.vcache = kc + (int64_t)B * L.nkv * W.Tmax * D * es;
+    at.kv_b_stride = (int64_t)L.nkv * W.Tmax * D; at.kv_h_stride = (int64_t)W.Tmax * D; at.kv_t_stride = D;
+    at.out = ws + W.attn; at.ldo = H;
+    at.key_mask = s->has_prompt_mask ? (const int*)(ws + W.prompt_mask) : nullptr; at.mask_len = P; at.mask_ld = P;
+    at.ctrl = ctrl; at.B = B; at.nh = L.nh; at.nkv = L.nkv; at.q_len = q_len;
+    at.past_from_ctrl = prefill ? 0 : 1; at.past_len = 0; at.prefix = P;
+    at.cross = 0; at.kv_len = 0;
+    at.rope = c.rope; at.rope_cos = blob + L.rope_cos; at.rope_sin = blob + L.rope_sin;
+    at.kv_capacity = prefill ? q_len : W.Tmax;
+    at.scale = 0.125f;  // head_dim ** -0.5, applied inside SDPA (quirk Q1)
+    if (int e = launch_attention(at, c.dtype, st, pdl)) return e;
+    s->launches++;
+    if (int e = lin(ws + W.attn, H, lb + L.wo, H, H, nullptr, nullptr, EPI_RESIDUAL, x, x, H, M)) return e;
+    if (int e = lin(x, H, lb + L.wqc, H, H, (const float*)(blob + lb + L.ln2_w), (const float*)(blob + lb + L.ln2_b),
+                    EPI_STORE, nullptr, ws + W.qc, H, M)) return e;
+    AttnArgs ct = at;
+    ct.q = ws + W.qc; ct.ldq = H; ct.q_col0 = 0;
+    ct.knew = ct.vnew = nullptr;
+    char* ck = ws + W.cross_kv + W.cross_layer_stride * i;
+    ct.kcache = ck; ct.vcache = ck + (int64_t)L.nckv * D * es;
+    ct.kv_b_stride = (int64_t)S * L.ckv_rows; ct.kv_h_stride = D; ct.kv_t_stride = L.ckv_rows;
+    ct.key_mask = s->has_enc_mask ? (const int*)(ws + W.enc_mask) : nullptr; ct.mask_len = S; ct.mask_ld = S;
+    ct.nkv = L.nckv; ct.cross = 1; ct.kv_len = S; ct.kv_capacity = S;
+    if (int e = launch_attention(ct, c.dtype, st, pdl)) return e;
+    s->launches++;
+    if (int e = lin(ws + W.attn, H, lb + L.woc, H, H, nullptr, nullptr, EPI_RESIDUAL, x, x, H, M)) return e;
+    if (int e = lin(x, H, lb + L.fc1, L.F, H, (const float*)(blob + lb + L.ln3_w), (const float*)(blob + lb + L.ln3_b),
+                    EPI_ACT, nullptr, ws + W.hbuf, L.F, M)) return e;
+    if (int e = lin(ws + W.hbuf, L.F, lb + L.fc2, H, L.F, nullptr, nullptr, EPI_RESIDUAL, x, x, H, M)) return e;
+  }
+  // final LayerNorm + K lm heads on the last position of every batch row -> f32 logits [B, K*V] == [B*K, V]
+  const char* xlast = ws + W.x + (int64_t)(q_len - 1) * H * es;
+  return lin(xlast, (int64_t)q_len * H, L.heads, L.K * L.V, H, (const float*)(blob + L.final_ln_w), (const float*)(blob + L.final_ln_b),
+             EPI_F32, nullptr, ws + W.logits, (int64_t)L.K * L.V, B);
+}
+
+int ptts_prefill(ptts_session* s, const void* prompt_hidden, const int64_t* prompt_mask, const void* enc_hidden,
+                 const int64_t* enc_mask, void* stream) {
+  PTTS_REQUIRE(s && enc_hidden, "null argument");
+  if (!s->begun) return fail(PTTS_ESTATE, "ptts_prefill called before ptts_generate_begin");
+  PTTS_REQUIRE(s->W.P == 0 || prompt_hidden, "prefill: prompt_hidden is required when P > 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  s->has_prompt_mask = (prompt_mask != nullptr && s->W.P > 0);
+  s->has_enc_mask = (enc_mask != nullptr);
+  if (s->has_prompt_mask) { if (int e = launch_mask_convert(prompt_mask, s->W.B * s->W.P, (int*)(s->ws + s->W.prompt_mask), st)) return e; }
+  if (s->has_enc_mask) { if (int e = launch_mask_convert(enc_mask, s->W.B * s->W.S, (int*)(s->ws + s->W.enc_mask), st)) return e; }
+  if (int e = run_forward(s, st, true, prompt_hidden, enc_hidden)) return e;
+  s->prefilled = true;
+  // mask presence is baked into the captured graph: re-capture if it changed
+  if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; s->graph_ready = false; }
+  return PTTS_OK;
+}
+
+int ptts_decode_forward(ptts_session* s, void* stream) {
+  PTTS_REQUIRE(s, "null argument");
+  if (!s->prefilled) return fail(PTTS_ESTATE, "ptts_decode_forward called before ptts_prefill");
+  return run_forward(s, (cudaStream_t)stream, false, nullptr, nullptr);
+}
+
+int ptts_sample(ptts_session* s, const int64_t* forced_tokens, void* stream) {
+  PTTS_REQUIRE(s, "null argument");
+  if (!s->prefilled) return fail(PTTS_ESTATE, "ptts_sample called before ptts_prefill");
+  s->launches++;
+  return launch_sample(sample_args(s), forced_tokens, (cudaStream_t)stream, false);
+}
+
+int ptts_decode_steps(ptts_session* s, int32_t n_steps, void* stream) {
+  PTTS_REQUIRE(s && n_steps >= 0, "bad argument");
+  if (!s->prefilled) return fail(PTTS_ESTATE, "ptts_decode_steps called before ptts_prefill");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!s->use_graph) {
+    for (int i = 0; i < n_steps; i++) {
+      if (int e = run_forward(s, st, false, nullptr, nullptr)) return e;
+      s->launches++;
+      if (int e = launch_sample(sample_args(s), nullptr, st, s->pdl)) return e;
+    }
+    return PTTS_OK;
+  }
+  if (!s->graph_ready) {
+    if (!s->cap_stream) PTTS_CHECK_CUDA(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+    const int64_t before = s->launches;
+    PTTS_CHECK_CUDA(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int e = run_forward(s, s->cap_stream, false, nullptr, nullptr);
+    if (!e) { s->launches++; e = launch_sample(sample_args(s), nullptr, s->cap_stream, s->pdl); }
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(s->cap_stream, &graph);
+    s->launches = before;
+    if (e) { if (graph) cudaGraphDestroy(graph); return e; }
+    if (ce != cudaSuccess) return fail(PTTS_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&s->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail(PTTS_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+    s->graph_ready = true;
+  }
+  const int per_step = 2 + 8 * s->L.L + 1;  // embed + 8 kernels/layer + heads + sample
+  for (int i = 0; i < n_steps; i++) PTTS_CHECK_CUDA(cudaGraphLaunch(s->exec, st));
+  s->launches += (int64_t)per_step * n_steps;
+  return PTTS_OK;
+}
+
+int ptts_session_logits(ptts_session* s, float** out) { PTTS_REQUIRE(s && out, "null"); *out = (float*)(s->ws + s->W.logits); return PTTS_OK; }
+int ptts_session_scores(ptts_session* s, float** out) { PTTS_REQUIRE(s && out, "null"); *out = (float*)(s->ws + s->W.scores); return PTTS_OK; }
+int ptts_session_raw_ids(ptts_session* s, int64_t** out, int32_t* ld) {
+  PTTS_REQUIRE(s && out && ld, "null");
+  *out = (int64_t*)(s->ws + s->W.raw_ids);
+  *ld = (int32_t)s->W.raw_ld;
+  return PTTS_OK;
+}
+int ptts_session_state(ptts_session* s, int32_t** out) { PTTS_REQUIRE(s && out, "null"); *out = (int32_t*)(s->ws + s->W.ctrl); return PTTS_OK; }
+int ptts_session_launches(ptts_session* s, int64_t* out) { PTTS_REQUIRE(s && out, "null"); *out = s->launches; return PTTS_OK; }
+
+// ---- stand-alone operators ----------------------------------------------------------------------
+int ptts_delay_build(const int64_t* input_ids, int32_t BK, int32_t seq_len, int32_t num_codebooks, int64_t bos, int64_t pad,
+                     int32_t max_length, int64_t* pattern_mask, void* stream) {
+  PTTS_REQUIRE(input_ids && pattern_mask, "null argument");
+  PTTS_REQUIRE(num_codebooks > 0 && BK > 0 && BK % num_codebooks == 0 && seq_len > 0 && max_length > 0, "delay_build: bad shape");
+  return launch_delay_build(input_ids, BK, seq_len, num_codebooks, bos, pad, max_length, pattern_mask, (cudaStream_t)stream);
+}
+int ptts_delay_apply(const int64_t* input_ids, int32_t BK, int32_t seq_len, int64_t ld_ids, const int64_t* pattern_mask,
+                     int64_t ld_mask, int64_t* out, void* stream) {
+  PTTS_REQUIRE(input_ids && pattern_mask && out, "null argument");
+  PTTS_REQUIRE(BK > 0 && seq_len > 0 && ld_mask >= seq_len && ld_ids >= seq_len, "delay_apply: mask shorter than ids");
+  return launch_delay_apply(input_ids, BK, seq_len, ld_ids, pattern_mask, ld_mask, out, (cudaStream_t)stream);
+}
+int ptts_logits_processor(const int64_t* input_ids, int32_t BK, int32_t seq_len, int64_t ld_ids, float* scores, int32_t V,
+                          int64_t eos, int32_t num_codebooks, int64_t* first_unfinished, void* stream) {
+  PTTS_REQUIRE(input_ids && scores && first_unfinished, "null argument");
+  return launch_logits_processor(input_ids, BK, seq_len, ld_ids, scores, V, eos, num_codebooks, first_unfinished, (cudaStream_t)stream);
+}
+
+int ptts_op_linear(const ptts_decoder_config* cfg, const void* blob, int32_t tensor_id, int32_t index, const void* x, int32_t M,
+                   int32_t use_ln, int32_t epilogue, const void* residual, void* y, void* stream) {
+  PTTS_REQUIRE(cfg && blob && x && y, "null argument");
+  if (int e = validate_config(*cfg)) return e;
+  const DecoderLayout L = make_layout(*cfg);
+  MatSlot ms;
+  PTTS_REQUIRE(matrix_slot(L, tensor_id, index, &ms), "op_linear: tensor %d is not a matrix", tensor_id);
+  const int64_t lb = L.layer0 + L.layer_stride * index;
+  LinearArgs a{};
+  a.X = x; a.ldx = ms.K; a.W = (const char*)blob + ms.off; a.Y = y; a.ldy = ms.N; a.R = residual; a.ldr = ms.N;
+  if (use_ln) {
+    PTTS_REQUIRE(ms.K == L.H, "op_linear: LayerNorm needs K == hidden_size");
+    int64_t w = 0, b = 0;
+    switch (tensor_id) {
+      case PTTS_T_SELF_Q: case PTTS_T_SELF_K: case PTTS_T_SELF_V: w = lb + L.ln1_w; b = lb + L.ln1_b; break;
+      case PTTS_T_CROSS_Q: w = lb + L.ln2_w; b = lb + L.ln2_b; break;
+      case PTTS_T_FC1: w = lb + L.ln3_w; b = lb + L.ln3_b; break;
+      case PTTS_T_LM_HEAD: w = L.final_ln_w; b = L.final_ln_b; break;
+      default: return fail(PTTS_EINVAL, "op_linear: tensor %d has no LayerNorm in front", tensor_id);
+    }
+    a.ln_w = (const float*)((const char*)blob + w);
+    a.ln_b = (const float*)((const char*)blob + b);
+  }
+  a.eps = cfg->layer_norm_eps;
+  a.M = M; a.N = ms.N; a.K = ms.K; a.Kc = (ms.K > L.H && ms.K % L.H == 0) ? L.H : ms.K;
+  a.epi = epilogue; a.act = cfg->activation; a.ctrl = nullptr;
+  PTTS_REQUIRE(epilogue >= 0 && epilogue <= 3, "op_linear: bad epilogue");
+  PTTS_REQUIRE(epilogue != EPI_RESIDUAL || residual, "op_linear: residual required");
+  int sm = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+  return launch_linear(a, cfg->dtype, (cudaStream_t)stream, false, sm);
+}
+
+// ---- DAC ----------------------------------------------------------------------------------------
+int ptts_dac_blob_bytes(const ptts_dac_config* cfg, int64_t* out_bytes) {
+  PTTS_REQUIRE(cfg && out_bytes, "null argument");
+  if (int e = validate_dac(*cfg)) return e;
+  *out_bytes = make_dac_layout(*cfg).total;
+  return PTTS_OK;
+}
+int ptts_dac_num_tensors(const ptts_dac_config* cfg, int32_t* out) {
+  PTTS_REQUIRE(cfg && out, "null argument");
+  if (int e = validate_dac(*cfg)) return e;
+  *out = (int32_t)make_dac_layout(*cfg).t.size();
+  return PTTS_OK;
+}
+int ptts_dac_pack(const ptts_dac_config* cfg, void* blob, int32_t name_id, const void* src, int32_t src_dtype, int64_t numel, void* stream) {
+  PTTS_REQUIRE(cfg && blob && src, "null argument");
+  if (int e = validate_dac(*cfg)) return e;
+  PTTS_REQUIRE(src_dtype == PTTS_BF16 || src_dtype == PTTS_F32, "dac pack: src dtype must be bf16 or f32");
+  const DacLayout L = make_dac_layout(*cfg);
+  PTTS_REQUIRE(name_id >= 0 && name_id < (int)L.t.size(), "dac pack: tensor id %d out of range", name_id);
+  const DacTensor& t = L.t[name_id];
+  PTTS_REQUIRE(numel == t.numel, "dac pack: tensor %d expects %lld elements, got %lld", name_id, (long long)t.numel, (long long)numel);
+  char* dst = (char*)blob + t.off;
+  if (t.kind == DK_PLAIN) return pack_plain(src, src_dtype, numel, dst, cfg->dtype, (cudaStream_t)stream);
+  return pack_conv(src, src_dtype, dst, cfg->dtype, t.d0, t.d1, t.k, t.kind == DK_CONVT, (cudaStream_t)stream);
+}
+int ptts_dac_workspace_bytes(const ptts_dac_config* cfg, int32_t B, int32_t T, int64_t* out_bytes) {
+  PTTS_REQUIRE(cfg && out_bytes && B > 0 && T > 0, "bad argument");
+  if (int e = validate_dac(*cfg)) return e;
+  *out_bytes = 2 * align_up(dac_max_act_per_frame(*cfg) * B * T * dtype_size(cfg->dtype), 256);
+  return PTTS_OK;
+}
+
+int ptts_dac_decode(const ptts_dac_config* cfg, const void* blob, void* workspace, int64_t workspace_bytes, const int64_t* codes,
+                    int32_t B, int32_t T, void* audio_out, void* stream) {
+  PTTS_REQUIRE(cfg && blob && workspace && codes && audio_out, "null argument");
+  if (int e = validate_dac(*cfg)) return e;
+  PTTS_REQUIRE(B > 0 && T > 0, "dac decode: empty input B=%d T=%d", B, T);
+  const DacLayout L = make_dac_layout(*cfg);
+  const int es = L.es;
+  const int64_t half = align_up(dac_max_act_per_frame(*cfg) * B * T * es, 256);
+  PTTS_REQUIRE(workspace_bytes >= 2 * half, "dac decode: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const char* bl = (const char*)blob;
+  char* cur = (char*)workspace;
+  char* oth = cur + half;
+  const int K = cfg->n_codebooks;
+  FromCodesArgs fc{codes, bl + L.codebooks, bl + L.proj_w, bl + L.proj_b, cur, K, cfg->codebook_dim, cfg->latent_dim, T, cfg->codebook_size};
+  if (int e = launch_from_codes(fc, cfg->dtype, B, st)) return e;
+  int ti = 3 * K;  // tensor cursor (see make_dac_layout order)
+  auto tp = [&](int i) { return bl + L.t[i].off; };
+  auto conv = [&](const void* x, int w_i, int b_i, const void* alpha, const void* res, void* out, int Cin, int Cout, int Tlen, int ks, int dil, int tanh_out) {
+    ConvArgs a{};
+    a.x = x; a.w = tp(w_i); a.bias = tp(b_i); a.alpha = alpha; a.res = res; a.out = out;
+    a.Cin = Cin; a.Cout = Cout; a.Tin = Tlen; a.Tout = Tlen; a.q_count = Tlen;
+    a.n_taps = ks; a.off_base = -((ks - 1) / 2) * dil; a.off_step = dil; a.wt_base = 0; a.wt_step = 1;
+    a.n_phase = 1; a.wt_phase_step = 0; a.o_mul = 1; a.o_add = 0; a.o_phase_step = 0; a.tanh_out = tanh_out;
+    return launch_conv(a, cfg->dtype, B, st);
+  };
+  const int C = cfg->decoder_dim;
+  if (int e = conv(cur, ti, ti + 1, nullptr, nullptr, oth, cfg->latent_dim, C, T, 7, 1, 0)) return e;
+  ti += 2;
+  std::swap(cur, oth);
+  int Tlen = T;
+  for (int bi = 0; bi < cfg->n_blocks; bi++) {
+    const int cin = C >> bi, cout = C >> (bi + 1), sd = cfg->strides[bi];
+    const int pad = (sd + 1) / 2;
+    ConvArgs a{};
+    a.x = cur; a.alpha = tp(ti); a.w = tp(ti + 1); a.bias = tp(ti + 2); a.res = nullptr; a.out = oth;
+    a.Cin = cin; a.Cout = cout; a.Tin = Tlen; a.Tout = Tlen * sd; a.q_count = Tlen + 1;
+    a.n_taps = 2; a.off_base = 0; a.off_step = -1; a.wt_base = 0; a.wt_step = sd;
+    a.n_phase = sd; a.wt_phase_step = 1; a.o_mul = sd; a.o_add = -pad; a.o_phase_step = 1; a.tanh_out = 0;
+    if (int e = launch_conv(a, cfg->dtype, B, st)) return e;
+    ti += 3;
+    std::swap(cur, oth);
+    Tlen *= sd;
+    const int dil[3] = {1, 3, 9};
+    for (int r = 0; r < 3; r++) {
+      // y = conv7(snake1(x)) -> oth ; x = x + conv1(snake2(y)) in place
+      if (int e = conv(cur, ti + 1, ti + 2, tp(ti), nullptr, oth, cout, cout, Tlen, 7, dil[r], 0)) return e;
+      if (int e = conv(oth, ti + 4, ti + 5, tp(ti + 3), cur, cur, cout, cout, Tlen, 1, 1, 0)) return e;
+      ti += 6;
+    }
+  }
+  const int cl = C >> cfg->n_blocks;
+  return conv(cur, ti + 1, ti + 2, tp(ti), nullptr, audio_out, cl, 1, Tlen, 7, 1, 1);
+}
+
+}  // extern "C"

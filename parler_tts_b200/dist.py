@@ -1,0 +1,51 @@
+"""Multi-GPU: one process per GPU, the generation batch sharded by utterance.
+
+The path has no per-step exchange -- utterances are independent -- so the only collective is one
+broadcast of the packed weight blobs from rank 0 at init (NCCL over NVLink on GPUs; the same code runs
+on gloo/CPU tensors in the world_size-2 unit tests).  Sampling uses per-row Philox substreams keyed by
+the GLOBAL row index, so results do not depend on the number of shards.
+"""
+from __future__ import annotations
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced rows [lo, hi) of rank; the first n % world ranks take one extra row."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(tensors: dict, rank: int, world: int) -> dict:
+    """Slice every [B, ...] tensor of a generate() kwarg dict to this rank's utterances."""
+    B = next(v.shape[0] for v in tensors.values() if isinstance(v, torch.Tensor))
+    lo, hi = shard_range(B, rank, world)
+    return {k: (v[lo:hi] if isinstance(v, torch.Tensor) and v.shape[0] == B else v) for k, v in tensors.items()}
+
+
+def broadcast_blob(blob: torch.Tensor, src: int = 0, group=None) -> torch.Tensor:
+    """One collective at init: ship the packed (already repacked) weight bytes from `src` to every rank."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(blob, src=src, group=group)
+    return blob
+
+
+def broadcast_model_weights(model, src: int = 0, group=None):
+    """Rank `src` has loaded/packed the checkpoint; the others only allocated blobs of the same size."""
+    broadcast_blob(model.decoder.engine.blob, src, group)
+    if model.audio_encoder.blob is not None:
+        broadcast_blob(model.audio_encoder.blob, src, group)
+    if model.embed_prompts_weight is not None:
+        broadcast_blob(model.embed_prompts_weight, src, group)
+    return model
+
+
+def gather_ragged_audio(audio: torch.Tensor, lengths: list[int], group=None):
+    """Host-side concatenation of per-rank ragged outputs -> (list of [n_i] tensors in global batch order)."""
+    local = [audio[i, : lengths[i]].cpu() for i in range(audio.shape[0])]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, local, group=group)
+    return [a for part in out for a in part]
