@@ -506,9 +506,11 @@ class ParlerTTSForConditionalGeneration:
         codes = output_ids[keep].reshape(B, K, -1)
         audio_codes = codes[None, ...]  # frame dim (:3600)
 
-        special = {d.bos_token_id, d.pad_token_id, d.eos_token_id}
-        decode_sequentially = bool(sum((audio_codes == t).any() for t in special))
+        # The reference decodes sample by sample when any bos/pad/eos id survived (:3615-3619).  Ids in
+        # (codebook_size, vocab) other than those (reachable on untrained weights, quirk Q5) would make its
+        # embedding lookup fail; here any id >= codebook_size takes the per-sample filtering path.
         cs = self.config.audio_encoder.codebook_size
+        decode_sequentially = bool((audio_codes >= cs).any())
         if not decode_sequentially and codes.shape[-1] > 0:
             vals = self.audio_encoder.decode(audio_codes=audio_codes, audio_scales=[None] * B).audio_values.squeeze(1)
             lengths = [vals.shape[1]] * B
