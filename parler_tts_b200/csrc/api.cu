@@ -9,6 +9,7 @@
 #include "dac.h"
 #include "kernels.h"
 #include "layout.h"
+#include "step.h"
 
 namespace ptts {
 static thread_local std::string g_err;
@@ -45,6 +46,8 @@ struct ptts_session {
   cudaGraphExec_t exec;
   bool graph_ready;
   int64_t launches;  // kernels launched through this session (bench.py reports it)
+  bool fused;        // decode steps run as the single persistent kernel (step.cu) instead of 8L+3 kernels
+  StepParams sp;
 };
 
 extern "C" {
@@ -149,6 +152,7 @@ int ptts_session_create(const ptts_decoder_config* cfg, const void* blob, void* 
   s->exec = nullptr;
   s->cap_stream = nullptr;
   s->begun = s->prefilled = false;
+  s->fused = false;
   s->launches = 0;
   *out = s;
   return PTTS_OK;
@@ -178,6 +182,70 @@ static SampleArgs sample_args(ptts_session* s) {
   a.B = W.B; a.K = s->cfg.num_codebooks; a.V = s->cfg.vocab_size;
   a.bos = s->cfg.bos_token_id; a.pad = s->cfg.pad_token_id; a.eos = s->cfg.eos_token_id;
   return a;
+}
+
+
+// Fused-step schedule: largest n-tile count that keeps ~one task per CTA.
+static int pick_nt(int ntiles, int grid) {
+  const int cand[6] = {9, 6, 4, 3, 2, 1};
+  for (int i = 0; i < 6; i++)
+    if (ntiles % cand[i] == 0 && ntiles / cand[i] >= (grid * 8) / 10) return cand[i];
+  for (int i = 0; i < 6; i++)
+    if (ntiles % cand[i] == 0 && ntiles / cand[i] >= grid / 2) return cand[i];
+  return 1;
+}
+
+static bool setup_fused(ptts_session* s) {
+  const ptts_decoder_config& c = s->cfg;
+  const DecoderLayout& L = s->L;
+  const WorkspaceLayout& W = s->W;
+  if (c.dtype != PTTS_BF16 || W.B > 32 || !env_flag("PTTS_FUSED", true)) return false;
+  if (L.H % 64 != 0 || L.F % L.H != 0) return false;
+  StepParams& p = s->sp;
+  memset(&p, 0, sizeof(p));
+  p.B = W.B; p.H = L.H; p.F = L.F; p.V = L.V; p.K = L.K; p.L = L.L; p.nh = L.nh; p.nkv = L.nkv; p.nckv = L.nckv;
+  p.S = W.S; p.P = W.P; p.Tmax = W.Tmax; p.rope = c.rope; p.act = c.activation; p.qkv_rows = L.qkv_rows; p.ckv_rows = L.ckv_rows;
+  p.eps = c.layer_norm_eps; p.scale = 0.125f;
+  p.blob = s->blob;
+  p.embed = L.embed; p.pos = L.pos; p.layer0 = L.layer0; p.layer_stride = L.layer_stride;
+  p.ln1_w = L.ln1_w; p.ln1_b = L.ln1_b; p.wqkv = L.wqkv; p.wo = L.wo; p.ln2_w = L.ln2_w; p.ln2_b = L.ln2_b; p.wqc = L.wqc; p.woc = L.woc;
+  p.ln3_w = L.ln3_w; p.ln3_b = L.ln3_b; p.fc1 = L.fc1; p.fc2 = L.fc2;
+  p.final_ln_w = L.final_ln_w; p.final_ln_b = L.final_ln_b; p.heads = L.heads; p.rope_cos = L.rope_cos; p.rope_sin = L.rope_sin;
+  char* ws = s->ws;
+  p.x = (bf16*)(ws + W.x); p.qkv = (bf16*)(ws + W.qkv); p.attn = (bf16*)(ws + W.attn); p.qc = (bf16*)(ws + W.qc); p.hbuf = (bf16*)(ws + W.hbuf);
+  p.logits = (float*)(ws + W.logits);
+  p.cross_kv = ws + W.cross_kv; p.cross_layer_stride = W.cross_layer_stride;
+  p.self_kv = ws + W.self_kv; p.self_layer_stride = W.self_layer_stride;
+  p.prompt_mask = s->has_prompt_mask ? (const int*)(ws + W.prompt_mask) : nullptr;
+  p.enc_mask = s->has_enc_mask ? (const int*)(ws + W.enc_mask) : nullptr;
+  p.sa = sample_args(s);
+  p.bar = ((Ctrl*)(ws + W.ctrl))->bar;
+  const int G = s->sm_count;
+  p.nt_qkv = pick_nt(L.qkv_rows / 8, G);
+  p.nt_h = pick_nt(L.H / 8, G);
+  p.nt_fc1 = pick_nt(L.F / 8, G);
+  p.nt_heads = pick_nt(L.K * L.V / 8, G);
+  int ntmax = p.nt_qkv;
+  if (p.nt_h > ntmax) ntmax = p.nt_h;
+  if (p.nt_fc1 > ntmax) ntmax = p.nt_fc1;
+  if (p.nt_heads > ntmax) ntmax = p.nt_heads;
+  const int64_t tile = (int64_t)32 * (L.H + 8) * 2;
+  const int64_t red = (int64_t)8 * 32 * 8 * ntmax * 4;
+  int kvcap = W.Tmax > W.S ? W.Tmax : W.S;
+  p.attn_floats_per_half = (64 + 4 * 64 + 8 + kvcap + 3) / 4 * 4;
+  const int64_t att = (int64_t)2 * p.attn_floats_per_half * 4;
+  const int64_t budget = 200 * 1024 - 128 - (int64_t)2 * L.H * 4;
+  p.nbuf = (2 * tile <= budget) ? 2 : 1;
+  int64_t region = p.nbuf * tile;
+  if (red > region) region = red;
+  if (att > region) region = att;
+  region = align_up(region, 16);
+  if (region > budget) return false;  // e.g. very long caches: fall back to the multi-kernel path
+  p.tile_region_bytes = region;
+  p.sample_items = (L.V + 31) / 32;
+  if (p.sample_items > 72) return false;
+  p.do_sample_phase = 1;
+  return true;
 }
 
 int ptts_generate_begin(ptts_session* s, const ptts_gen_params* gen, void* stream) {
@@ -294,6 +362,7 @@ int ptts_prefill(ptts_session* s, const void* prompt_hidden, const int64_t* prom
   if (s->has_enc_mask) { if (int e = launch_mask_convert(enc_mask, s->W.B * s->W.S, (int*)(s->ws + s->W.enc_mask), st)) return e; }
   if (int e = run_forward(s, st, true, prompt_hidden, enc_hidden)) return e;
   s->prefilled = true;
+  s->fused = setup_fused(s);
   // mask presence is baked into the captured graph: re-capture if it changed
   if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; s->graph_ready = false; }
   return PTTS_OK;
@@ -302,6 +371,12 @@ int ptts_prefill(ptts_session* s, const void* prompt_hidden, const int64_t* prom
 int ptts_decode_forward(ptts_session* s, void* stream) {
   PTTS_REQUIRE(s, "null argument");
   if (!s->prefilled) return fail(PTTS_ESTATE, "ptts_decode_forward called before ptts_prefill");
+  if (s->fused) {
+    StepParams p = s->sp;
+    p.do_sample_phase = 0;
+    s->launches++;
+    return launch_decode_step(p, s->sm_count, (cudaStream_t)stream);
+  }
   return run_forward(s, (cudaStream_t)stream, false, nullptr, nullptr);
 }
 
@@ -316,6 +391,12 @@ int ptts_decode_steps(ptts_session* s, int32_t n_steps, void* stream) {
   PTTS_REQUIRE(s && n_steps >= 0, "bad argument");
   if (!s->prefilled) return fail(PTTS_ESTATE, "ptts_decode_steps called before ptts_prefill");
   cudaStream_t st = (cudaStream_t)stream;
+  if (s->fused) {  // one persistent kernel per token: nothing to gain from a graph
+    for (int i = 0; i < n_steps; i++)
+      if (int e = launch_decode_step(s->sp, s->sm_count, st)) return e;
+    s->launches += n_steps;
+    return PTTS_OK;
+  }
   if (!s->use_graph) {
     for (int i = 0; i < n_steps; i++) {
       if (int e = run_forward(s, st, false, nullptr, nullptr)) return e;

@@ -41,8 +41,12 @@ struct Ctrl {
   int n_unfinished;
   int done_blocks;    // last-block-done counter for ptts_sample
   int steps_run;      // decode steps actually executed (not no-op'd)
-  int pad_[3];
+  int launch_gen;     // fused step kernel launches so far (selects the barrier counter)
+  int pad_[26];
+  unsigned bar[2];    // device-wide barrier counters of the fused step kernel (own 128 B line)
+  unsigned pad2_[30];
 };
+static_assert(sizeof(Ctrl) == 256, "Ctrl layout");
 
 // ---- dtype traits -------------------------------------------------------------------------------
 template <typename T> struct DT;

@@ -1,0 +1,37 @@
+// step.h -- parameters of the fused decode-step kernel (step.cu).
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ptts {
+
+struct StepParams {
+  // shapes
+  int B, H, F, V, K, L, nh, nkv, nckv, S, P, Tmax, rope, act, qkv_rows, ckv_rows;
+  float eps, scale;
+  // packed weights
+  const char* blob;
+  int64_t embed, pos, layer0, layer_stride, ln1_w, ln1_b, wqkv, wo, ln2_w, ln2_b, wqc, woc, ln3_w, ln3_b, fc1, fc2;
+  int64_t final_ln_w, final_ln_b, heads, rope_cos, rope_sin;
+  // workspace
+  bf16 *x, *qkv, *attn, *qc, *hbuf;
+  float* logits;
+  char* cross_kv; int64_t cross_layer_stride;
+  char* self_kv; int64_t self_layer_stride;
+  const int* prompt_mask;  // nullable
+  const int* enc_mask;     // nullable
+  SampleArgs sa;
+  unsigned* bar;           // [2] device-wide barrier counters (Ctrl::bar)
+  // schedule
+  int nt_qkv, nt_h, nt_fc1, nt_heads;
+  int nbuf;                // activation-tile buffers (2 = double-buffered K chunks)
+  int attn_floats_per_half;
+  int64_t tile_region_bytes;
+  int do_sample_phase;     // 1: logits -> token inside the kernel (ptts_decode_steps); 0: stop at the logits
+  int sample_items;        // ceil(V / 32)
+};
+
+int step_smem_bytes(const StepParams& p);
+int launch_decode_step(const StepParams& p, int grid, cudaStream_t st);
+
+}  // namespace ptts

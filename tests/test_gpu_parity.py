@@ -440,3 +440,53 @@ def test_mini_shape_bf16_batch32_teacher_forced():
         total += a.shape[0]
         sess.sample(forced=torch.from_numpy(ref["raw_ids"][:, t + 1].copy()))
     assert agree / total > 0.9
+
+
+# ---- fused persistent step kernel (step.cu) vs the multi-kernel path -------------------------------
+def _free_run_bf16(cfg, w, B, S, P, L, fused, monkeypatch, gen=None, seed=3):
+    monkeypatch.setenv("PTTS_FUSED", "1" if fused else "0")
+    dcfg = tiny_dac_cfg(n_codebooks=cfg.num_codebooks, codebook_size=cfg.codebook_size)
+    model = build_product_model(cfg, dcfg, w, make_dac_weights(dcfg, seed=1), dtype=torch.bfloat16)
+    enc, enc_mask, prompt, prompt_mask = synth_inputs(cfg, B, S, P, seed=seed)
+    sess = model.decoder.engine.session(B, P, S, P + L)
+    sess.begin(L, **(gen or dict(do_sample=False)))
+    sess.prefill(prompt.to(DEV), prompt_mask, enc.to(DEV), enc_mask)
+    sess.sample()
+    sess.decode_steps(L - 2)
+    torch.cuda.synchronize()
+    n = int(sess.state[0].item())
+    return sess.raw_ids[:, :n].cpu().numpy().copy(), sess.logits.cpu().numpy().copy(), sess.launches
+
+
+@pytest.mark.parametrize("name", ["abs", "rope", "gqa"])
+def test_fused_step_equals_multikernel_bitwise(name, monkeypatch):
+    """Same arithmetic, same reduction order: tokens AND last-step logits are bit-identical."""
+    cfg = _variant(name)
+    w = make_decoder_weights(cfg, seed=81, head_std=0.5)
+    a_ids, a_log, a_launch = _free_run_bf16(cfg, w, 5, 9, 5, 36, True, monkeypatch)
+    b_ids, b_log, b_launch = _free_run_bf16(cfg, w, 5, 9, 5, 36, False, monkeypatch)
+    assert a_ids.shape == b_ids.shape and np.array_equal(a_ids, b_ids)
+    assert np.array_equal(a_log, b_log)
+    assert a_launch < b_launch / 10  # one kernel per token instead of 8L+3
+
+
+def test_fused_step_sampling_and_eos(monkeypatch):
+    cfg = tiny_cfg()
+    w = make_decoder_weights(cfg, seed=82, head_std=0.5)
+    for k in range(cfg.num_codebooks):
+        w[f"decoder.lm_heads.{k}.weight"][cfg.eos_token_id] *= 5.0
+    gen = dict(do_sample=True, top_k=12, temperature=0.9, top_p=0.95, seed=11)
+    a_ids, a_log, _ = _free_run_bf16(cfg, w, 4, 8, 4, 40, True, monkeypatch, gen)
+    b_ids, b_log, _ = _free_run_bf16(cfg, w, 4, 8, 4, 40, False, monkeypatch, gen)
+    assert (a_ids == cfg.eos_token_id).any()
+    assert np.array_equal(a_ids, b_ids) and np.array_equal(a_log, b_log)
+
+
+def test_fused_step_mini_shape_batch32(monkeypatch):
+    """BASELINE configs[1] shape: fused kernel == multi-kernel path over 20 free-running greedy steps."""
+    cfg = mini_cfg(max_position_embeddings=256)
+    w = make_decoder_weights(cfg, seed=83, head_std=0.2)
+    a_ids, a_log, _ = _free_run_bf16(cfg, w, 32, 16, 8, 22, True, monkeypatch)
+    b_ids, b_log, _ = _free_run_bf16(cfg, w, 32, 16, 8, 22, False, monkeypatch)
+    assert np.array_equal(a_ids, b_ids)
+    assert np.array_equal(a_log, b_log)
