@@ -46,6 +46,7 @@ struct ptts_session {
   cudaGraphExec_t exec;
   bool graph_ready;
   int64_t launches;  // kernels launched through this session (bench.py reports it)
+  long long* prof;
   bool fused;        // decode steps run as the single persistent kernel (step.cu) instead of 8L+3 kernels
   StepParams sp;
 };
@@ -153,6 +154,7 @@ int ptts_session_create(const ptts_decoder_config* cfg, const void* blob, void* 
   s->cap_stream = nullptr;
   s->begun = s->prefilled = false;
   s->fused = false;
+  s->prof = nullptr;
   s->launches = 0;
   *out = s;
   return PTTS_OK;
@@ -187,10 +189,10 @@ static SampleArgs sample_args(ptts_session* s) {
 
 // Fused-step schedule: largest n-tile count that keeps ~one task per CTA.
 static int pick_nt(int ntiles, int grid) {
-  const int cand[6] = {9, 6, 4, 3, 2, 1};
-  for (int i = 0; i < 6; i++)
+  const int cand[4] = {4, 3, 2, 1};  // the variants instantiated in step.cu::run_gemm
+  for (int i = 0; i < 4; i++)
     if (ntiles % cand[i] == 0 && ntiles / cand[i] >= (grid * 8) / 10) return cand[i];
-  for (int i = 0; i < 6; i++)
+  for (int i = 0; i < 4; i++)
     if (ntiles % cand[i] == 0 && ntiles / cand[i] >= grid / 2) return cand[i];
   return 1;
 }
@@ -199,7 +201,7 @@ static bool setup_fused(ptts_session* s) {
   const ptts_decoder_config& c = s->cfg;
   const DecoderLayout& L = s->L;
   const WorkspaceLayout& W = s->W;
-  if (c.dtype != PTTS_BF16 || W.B > 32 || !env_flag("PTTS_FUSED", true)) return false;
+  if (c.dtype != PTTS_BF16 || W.B > 32 || L.K > 16 || !env_flag("PTTS_FUSED", true)) return false;
   if (L.H % 64 != 0 || L.F % L.H != 0) return false;
   StepParams& p = s->sp;
   memset(&p, 0, sizeof(p));
@@ -220,6 +222,7 @@ static bool setup_fused(ptts_session* s) {
   p.enc_mask = s->has_enc_mask ? (const int*)(ws + W.enc_mask) : nullptr;
   p.sa = sample_args(s);
   p.bar = ((Ctrl*)(ws + W.ctrl))->bar;
+  p.progress = (int*)(ws + W.progress);
   const int G = s->sm_count;
   p.nt_qkv = pick_nt(L.qkv_rows / 8, G);
   p.nt_h = pick_nt(L.H / 8, G);
@@ -232,9 +235,10 @@ static bool setup_fused(ptts_session* s) {
   const int64_t tile = (int64_t)32 * (L.H + 8) * 2;
   const int64_t red = (int64_t)8 * 32 * 8 * ntmax * 4;
   int kvcap = W.Tmax > W.S ? W.Tmax : W.S;
-  p.attn_floats_per_half = (64 + 4 * 64 + 8 + kvcap + 3) / 4 * 4;
-  const int64_t att = (int64_t)2 * p.attn_floats_per_half * 4;
-  const int64_t budget = 200 * 1024 - 128 - (int64_t)2 * L.H * 4;
+  (void)kvcap;
+  p.attn_floats_per_warp = 0;
+  const int64_t att = (int64_t)8 * (2 * 2 * 32 * 64 * 2 + 3 * 64 * 4);  // 8 x attn_decode_smem_per_warp<bf16>()
+  const int64_t budget = 200 * 1024 - 256 - (int64_t)2 * L.H * 4;
   p.nbuf = (2 * tile <= budget) ? 2 : 1;
   int64_t region = p.nbuf * tile;
   if (red > region) region = red;
@@ -245,6 +249,7 @@ static bool setup_fused(ptts_session* s) {
   p.sample_items = (L.V + 31) / 32;
   if (p.sample_items > 72) return false;
   p.do_sample_phase = 1;
+  p.prof = s->prof;
   return true;
 }
 
@@ -306,7 +311,9 @@ static int run_forward(ptts_session* s, cudaStream_t st, bool prefill, const voi
     char* x = ws + W.x;
     if (prefill) {  // cross-attention K/V of the encoder states, once per generate() (:872-878)
       if (int e = lin(enc_hidden, H, lb + L.wkvc, L.ckv_rows, H, nullptr, nullptr, EPI_STORE, nullptr,
-                      ws + W.cross_kv + W.cross_layer_stride * i, L.ckv_rows, B * S)) return e;
+                      ws + W.cross_tmp, L.ckv_rows, B * S)) return e;
+      if (int e = launch_cross_kv_relayout(ws + W.cross_tmp, ws + W.cross_kv + W.cross_layer_stride * i, B, S, L.nckv, c.dtype, st)) return e;
+      s->launches++;
     }
     if (int e = lin(x, H, lb + L.wqkv, L.qkv_rows, H, (const float*)(blob + lb + L.ln1_w), (const float*)(blob + lb + L.ln1_b),
                     EPI_STORE, nullptr, ws + W.qkv, L.qkv_rows, M)) return e;
@@ -333,8 +340,8 @@ static int run_forward(ptts_session* s, cudaStream_t st, bool prefill, const voi
     ct.q = ws + W.qc; ct.ldq = H; ct.q_col0 = 0;
     ct.knew = ct.vnew = nullptr;
     char* ck = ws + W.cross_kv + W.cross_layer_stride * i;
-    ct.kcache = ck; ct.vcache = ck + (int64_t)L.nckv * D * es;
-    ct.kv_b_stride = (int64_t)S * L.ckv_rows; ct.kv_h_stride = D; ct.kv_t_stride = L.ckv_rows;
+    ct.kcache = ck; ct.vcache = ck + (int64_t)B * L.nckv * S * D * es;   // item-major: K [B][nckv][S][64] | V [...]
+    ct.kv_b_stride = (int64_t)L.nckv * S * D; ct.kv_h_stride = (int64_t)S * D; ct.kv_t_stride = D;
     ct.key_mask = s->has_enc_mask ? (const int*)(ws + W.enc_mask) : nullptr; ct.mask_len = S; ct.mask_ld = S;
     ct.nkv = L.nckv; ct.cross = 1; ct.kv_len = S; ct.kv_capacity = S;
     if (int e = launch_attention(ct, c.dtype, st, pdl)) return e;
@@ -436,6 +443,14 @@ int ptts_session_raw_ids(ptts_session* s, int64_t** out, int32_t* ld) {
   return PTTS_OK;
 }
 int ptts_session_state(ptts_session* s, int32_t** out) { PTTS_REQUIRE(s && out, "null"); *out = (int32_t*)(s->ws + s->W.ctrl); return PTTS_OK; }
+// Debug / profiling aid: CTA 0 of the fused step kernel writes clock64() stamps per phase into `buf`
+// (device int64 [(8L+2)*8]); pass NULL to switch it off.  Only the next launches are affected.
+int ptts_session_set_profile(ptts_session* s, void* buf) {
+  PTTS_REQUIRE(s, "null");
+  s->prof = (long long*)buf;
+  s->sp.prof = s->prof;
+  return PTTS_OK;
+}
 int ptts_session_launches(ptts_session* s, int64_t* out) { PTTS_REQUIRE(s && out, "null"); *out = s->launches; return PTTS_OK; }
 
 // ---- stand-alone operators ----------------------------------------------------------------------

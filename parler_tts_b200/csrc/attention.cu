@@ -25,7 +25,48 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnArgs p) {
   attention_item<T>(p, blockIdx.y, blockIdx.x, sm, threadIdx.x, [] { __syncthreads(); });
 }
 
+// decode (q_len == 1): 8 items per CTA, one warp each (TMA-staged K/V ring per warp)
+template <typename T>
+__global__ void __launch_bounds__(256) attention_decode_kernel(AttnArgs p) {
+  extern __shared__ __align__(128) unsigned char smd[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smd) + 2 * warp;  // 128 B header: 8 warps x 2 mbarriers
+  unsigned char* sm_warp = smd + 128 + (size_t)warp * attn_decode_smem_per_warp<T>();
+  attention_decode_init_warp(bars, lane);
+  pdl_launch_dependents();
+  pdl_wait();
+  if (p.ctrl != nullptr && p.ctrl->active == 0) return;
+  const int it = blockIdx.x * 8 + warp;
+  if (it >= p.B * p.nkv) return;
+  int past = p.past_len;
+  if (p.past_from_ctrl) past = p.prefix + p.ctrl->cur_len - 1;
+  uint32_t parity = 0;
+  attention_decode_item_warp<T>(p, it / p.nkv, it % p.nkv, past, sm_warp, bars, lane, parity);
+}
+
 int launch_attention(const AttnArgs& a, int dtype, cudaStream_t st, bool pdl) {
+  if (a.q_len == 1) {
+    const size_t smem_d = 128 + (size_t)8 * (dtype == PTTS_BF16 ? attn_decode_smem_per_warp<bf16>() : attn_decode_smem_per_warp<float>());
+    static bool attr_d = false;
+    if (!attr_d) {
+      PTTS_CHECK_CUDA(cudaFuncSetAttribute(attention_decode_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      PTTS_CHECK_CUDA(cudaFuncSetAttribute(attention_decode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_d = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((a.B * a.nkv + 7) / 8);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem_d;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (dtype == PTTS_BF16) PTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attention_decode_kernel<bf16>, a));
+    else PTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attention_decode_kernel<float>, a));
+    return PTTS_OK;
+  }
   const int kv_capacity = a.kv_capacity;
   PTTS_REQUIRE(a.B > 0 && a.nkv > 0 && a.q_len > 0, "attention: empty problem");
   const size_t smem = (size_t)(HD + ATT_WARPS * HD + 8 + kv_capacity) * sizeof(float);

@@ -76,4 +76,26 @@ int launch_gather_rows(const void* src, int64_t ld_src, int64_t row0, int64_t ro
   return PTTS_OK;
 }
 
+// cross-attention K/V: GEMM output rows [B*S][K(nckv*64) | V(nckv*64)] -> item-major K [B][nckv][S][64] then
+// V [B][nckv][S][64], so a (batch row, kv head) item is ONE contiguous run the TMA engine fetches with a
+// single bulk copy per stage (done once per generate() at prefill; reference keeps [B, heads, S, 64] too, :877-878).
+template <typename T>
+__global__ void cross_kv_relayout_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int S, int nckv) {
+  const int row = blockIdx.x;  // b*S + s
+  const int b = row / S, sidx = row - b * S;
+  const int width = 2 * nckv * 64;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    const int is_v = c >= nckv * 64;
+    const int cc = c - is_v * nckv * 64;
+    const int h = cc >> 6, d = cc & 63;
+    dst[(size_t)is_v * B * nckv * S * 64 + (((size_t)b * nckv + h) * S + sidx) * 64 + d] = src[(size_t)row * width + c];
+  }
+}
+int launch_cross_kv_relayout(const void* src, void* dst, int B, int S, int nckv, int dtype, cudaStream_t st) {
+  if (dtype == PTTS_BF16) cross_kv_relayout_kernel<bf16><<<B * S, 128, 0, st>>>((const bf16*)src, (bf16*)dst, B, S, nckv);
+  else cross_kv_relayout_kernel<float><<<B * S, 128, 0, st>>>((const float*)src, (float*)dst, B, S, nckv);
+  PTTS_LAUNCH_CHECK();
+  return PTTS_OK;
+}
+
 }  // namespace ptts

@@ -44,28 +44,40 @@ constexpr int GEMM_WARPS = 8;
 constexpr int TILE_M = 32;
 
 // In-place LayerNorm of the staged tile (rows x Kc, row stride lds), fp32 two-pass statistics.
+// Same lane->element mapping and summation order as step.cu::ln_tile (the two paths are compared bitwise).
+__device__ __forceinline__ void unpack8g(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
 __device__ void tile_layernorm(bf16* xs, int lds, int Kc, const float* __restrict__ g, const float* __restrict__ b, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < TILE_M; r += GEMM_WARPS) {
     bf16* row = xs + r * lds;
     float s = 0.f;
-    for (int c = lane * 2; c < Kc; c += 64) {
-      float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + c));
-      s += v.x + v.y;
+    for (int c = lane * 8; c < Kc; c += 256) {
+      float f[8];
+      unpack8g(*reinterpret_cast<const uint4*>(row + c), f);
+      s += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
     }
     const float mean = warp_sum(s) / (float)Kc;
     float q = 0.f;
-    for (int c = lane * 2; c < Kc; c += 64) {
-      float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + c));
-      float a = v.x - mean, d = v.y - mean;
-      q += a * a + d * d;
+    for (int c = lane * 8; c < Kc; c += 256) {
+      float f[8];
+      unpack8g(*reinterpret_cast<const uint4*>(row + c), f);
+#pragma unroll
+      for (int e = 0; e < 8; e++) { const float d = f[e] - mean; q = fmaf(d, d, q); }
     }
     const float rstd = rsqrtf(warp_sum(q) / (float)Kc + eps);
-    for (int c = lane * 2; c < Kc; c += 64) {
-      float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + c));
-      float y0 = (v.x - mean) * rstd * g[c] + b[c];
-      float y1 = (v.y - mean) * rstd * g[c + 1] + b[c + 1];
-      *reinterpret_cast<__nv_bfloat162*>(row + c) = __floats2bfloat162_rn(y0, y1);
+    for (int c = lane * 8; c < Kc; c += 256) {
+      float f[8];
+      unpack8g(*reinterpret_cast<const uint4*>(row + c), f);
+      uint4 o;
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        oh[e] = __floats2bfloat162_rn((f[2 * e] - mean) * rstd * g[c + 2 * e] + b[c + 2 * e], (f[2 * e + 1] - mean) * rstd * g[c + 2 * e + 1] + b[c + 2 * e + 1]);
+      *reinterpret_cast<uint4*>(row + c) = o;
     }
   }
 }

@@ -100,8 +100,8 @@ static inline bool matrix_slot(const DecoderLayout& l, int tensor_id, int index,
 // ---- workspace ----------------------------------------------------------------------------------
 struct WorkspaceLayout {
   int B, P, S, Tmax, Mmax, BK;
-  int64_t ctrl, gen, raw_ids, cur_ids, eos_seen, unfinished, first_unf, prompt_mask, enc_mask;
-  int64_t x, qkv, attn, qc, hbuf, hidden, logits, scores, cross_kv, self_kv;
+  int64_t ctrl, progress, gen, raw_ids, cur_ids, eos_seen, unfinished, first_unf, prompt_mask, enc_mask;
+  int64_t x, qkv, attn, qc, hbuf, hidden, logits, scores, cross_tmp, cross_kv, self_kv;
   int64_t cross_layer_stride, self_layer_stride;  // bytes
   int64_t raw_ld;                                  // raw_ids leading dimension (elements)
   int64_t total;
@@ -115,6 +115,7 @@ static inline WorkspaceLayout make_workspace(const ptts_decoder_config& c, int B
   int64_t o = 0;
   auto take = [&](int64_t bytes) { int64_t r = o; o = align_up(o + bytes, 256); return r; };
   w.ctrl = take(sizeof(Ctrl));
+  w.progress = take(1024 * 4);
   w.gen = take(sizeof(ptts_gen_params));
   w.raw_ld = Tmax - P + 1;  // >= max_length
   w.raw_ids = take((int64_t)w.BK * w.raw_ld * 8);
@@ -134,6 +135,7 @@ static inline WorkspaceLayout make_workspace(const ptts_decoder_config& c, int B
   w.logits = take((int64_t)w.BK * l.V * 4);
   w.scores = take((int64_t)w.BK * l.V * 4);
   w.cross_layer_stride = align_up(rows_enc * l.ckv_rows * l.es, 256);
+  w.cross_tmp = take(w.cross_layer_stride);   // GEMM output of one layer before the item-major re-layout
   w.cross_kv = take(w.cross_layer_stride * l.L);
   w.self_layer_stride = align_up((int64_t)2 * B * l.nkv * Tmax * PTTS_HEAD_DIM * l.es, 256);
   w.self_kv = take(w.self_layer_stride * l.L);

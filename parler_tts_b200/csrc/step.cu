@@ -38,16 +38,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  uint32_t spins = 0;
   do {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 22)) { printf("ptts: tile mbarrier timeout (cta %d)\n", (int)blockIdx.x); __trap(); }
   } while (!ok);
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// orders this thread's prior generic-proxy accesses (shared AND the acquired global data) before later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
   const char* c = reinterpret_cast<const char*>(p);
   while (bytes > 0) {
@@ -57,11 +60,15 @@ __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
     bytes -= n;
   }
 }
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void ldmatrix_x4s(uint32_t (&r)[4], const void* smem_ptr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_ptr)));
@@ -78,21 +85,31 @@ __device__ __forceinline__ uint4 ldg_stream_s(const uint4* p) {
 }
 
 // ---- device-wide barrier ------------------------------------------------------------------------
-struct GridBar {
-  unsigned* ctr;
-  unsigned target;
-  __device__ __forceinline__ void sync() {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      target += gridDim.x;
-      __threadfence();
-      atomicAdd(ctr, 1u);
-      while (ld_acquire(ctr) < target) {}
-      __threadfence();
+// Arrive = red.release (cumulative over the CTA's writes ordered by the preceding bar.sync); the spin is a
+// RELAXED load (an acquire load would invalidate L1 on every poll); one acquire fence after the exit.
+__device__ __forceinline__ unsigned grid_sync(unsigned* ctr, unsigned target, int* progress = nullptr, int ph = 0) {
+  target += gridDim.x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (progress) progress[blockIdx.x] = ph;
+    red_release_add(ctr, 1u);
+    unsigned spins = 0;
+    while (ld_relaxed(ctr) < target) {
+      if (++spins > (1u << 24)) {
+        printf("ptts: grid barrier timeout (cta %d target %u seen %u ph %d)\n", (int)blockIdx.x, target, ld_relaxed(ctr), ph);
+        if (progress) for (int i = 0; i < (int)gridDim.x; i++) if (((volatile int*)progress)[i] != ph) printf("ptts:   cta %d is at phase %d\n", i, ((volatile int*)progress)[i]);
+        __trap();
+      }
     }
-    __syncthreads();
+    fence_acq_rel_gpu();
   }
-};
+  __syncthreads();
+  return target;
+}
+
+__device__ __forceinline__ void prof_mark(long long* prof, int slot) {
+  if (prof != nullptr && threadIdx.x == 0) prof[slot] = clock64();
+}
 
 // ---- shared-memory context ----------------------------------------------------------------------
 struct Smem {
@@ -101,6 +118,7 @@ struct Smem {
   bf16* tile[2];    // activation tile buffers, row pitch = H + 8
   unsigned char* scratch;  // start of the tile region (aliased by the K-reduction buffer and by attention)
   uint32_t parity;  // bit i: parity to wait for on bars[i]
+  long long* prof;  // CTA 0 / thread 0 timestamps of the current phase (nullptr = off)
   int pitch;
   int nbuf;
 };
@@ -112,7 +130,10 @@ __device__ __forceinline__ void stage_tile(Smem& sm, int buf, const bf16* X, int
     fence_proxy_async();
     if (threadIdx.x == 0) mbar_expect_tx(&sm.bars[buf], (uint32_t)(M * Kc * 2));
     __syncwarp();
-    if ((int)threadIdx.x < M) bulk_g2s(sm.tile[buf] + (size_t)threadIdx.x * sm.pitch, X + (size_t)threadIdx.x * ldx + col0, (uint32_t)(Kc * 2), &sm.bars[buf]);
+    // one bulk copy per row (tools/ubench.cu: 1.23 us for the 64 KB tile with all 148 CTAs reading the same
+    // lines -- no L2 hot-spotting; splitting rows into more, staggered copies was 3x slower: per-copy cost)
+    if ((int)threadIdx.x < M)
+      bulk_g2s(sm.tile[buf] + (size_t)threadIdx.x * sm.pitch, X + (size_t)threadIdx.x * ldx + col0, (uint32_t)(Kc * 2), &sm.bars[buf]);
   }
 }
 __device__ __forceinline__ void wait_tile(Smem& sm, int buf) {
@@ -120,39 +141,61 @@ __device__ __forceinline__ void wait_tile(Smem& sm, int buf) {
   sm.parity ^= (1u << buf);
 }
 
-// In-place LayerNorm of the staged tile; each warp owns rows warp, warp+8, ...; values stay in registers.
+// In-place LayerNorm of the staged tile.  Each warp owns rows warp, warp+8, warp+16, warp+24 and walks them
+// TOGETHER (4 independent chains), 8 elements (one LDS.128) per lane per step; 3 passes over shared memory
+// (mean, variance, normalise -- the two-pass statistics torch uses), no per-thread arrays.
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
 __device__ __forceinline__ void ln_tile(bf16* xs, int pitch, int Kc, int M, const float* __restrict__ lnp, int H, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nj = Kc >> 6;  // bf16x2 per lane
-  for (int r = warp; r < M; r += ST_WARPS) {
-    bf16* row = xs + (size_t)r * pitch;
-    float2 v[32];
-    float s = 0.f;
+  bf16* row[4];
+  bool ok[4];
 #pragma unroll
-    for (int j = 0; j < 32; j++)
-      if (j < nj) {
-        v[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + lane * 2 + 64 * j));
-        s += v[j].x + v[j].y;
-      }
-    const float mean = warp_sum(s) / (float)Kc;
-    float q = 0.f;
+  for (int i = 0; i < 4; i++) { ok[i] = warp + 8 * i < M; row[i] = xs + (size_t)(warp + 8 * (ok[i] ? i : 0)) * pitch; }
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = lane * 8; c < Kc; c += 256) {
 #pragma unroll
-    for (int j = 0; j < 32; j++)
-      if (j < nj) {
-        const float a = v[j].x - mean, d = v[j].y - mean;
-        q += a * a + d * d;
-      }
-    const float rstd = rsqrtf(warp_sum(q) / (float)Kc + eps);
+    for (int i = 0; i < 4; i++) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(row[i] + c), f);
+      s[i] += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+    }
+  }
+  float mean[4], q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 32; j++)
-      if (j < nj) {
-        const int c = lane * 2 + 64 * j;
-        const float2 g = *reinterpret_cast<const float2*>(lnp + c);
-        const float2 bb = *reinterpret_cast<const float2*>(lnp + H + c);
-        const float y0 = (v[j].x - mean) * rstd * g.x + bb.x;
-        const float y1 = (v[j].y - mean) * rstd * g.y + bb.y;
-        *reinterpret_cast<__nv_bfloat162*>(row + c) = __floats2bfloat162_rn(y0, y1);
-      }
+  for (int i = 0; i < 4; i++) mean[i] = warp_sum(s[i]) / (float)Kc;
+  for (int c = lane * 8; c < Kc; c += 256) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(row[i] + c), f);
+#pragma unroll
+      for (int e = 0; e < 8; e++) { const float d = f[e] - mean[i]; q[i] = fmaf(d, d, q[i]); }
+    }
+  }
+  float rstd[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) rstd[i] = rsqrtf(warp_sum(q[i]) / (float)Kc + eps);
+  for (int c = lane * 8; c < Kc; c += 256) {
+    float g[8], bb[8];
+    *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(lnp + c);
+    *reinterpret_cast<float4*>(g + 4) = *reinterpret_cast<const float4*>(lnp + c + 4);
+    *reinterpret_cast<float4*>(bb) = *reinterpret_cast<const float4*>(lnp + H + c);
+    *reinterpret_cast<float4*>(bb + 4) = *reinterpret_cast<const float4*>(lnp + H + c + 4);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(row[i] + c), f);
+      uint4 o;
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        oh[e] = __floats2bfloat162_rn((f[2 * e] - mean[i]) * rstd[i] * g[2 * e] + bb[2 * e], (f[2 * e + 1] - mean[i]) * rstd[i] * g[2 * e + 1] + bb[2 * e + 1]);
+      if (ok[i]) *reinterpret_cast<uint4*>(row[i] + c) = o;
+    }
   }
 }
 
@@ -168,7 +211,7 @@ struct GemmDesc {
 
 // All tasks (n-blocks of 8*NT features) of one linear layer assigned to this CTA.  M = B <= 32 rows.
 template <int NT, int PF>
-__device__ __noinline__ void gemm_tasks(const StepParams& p, Smem& sm, const GemmDesc& d) {
+__device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const GemmDesc& d) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = p.B, H = p.H;
   const int Kc = d.K < H ? d.K : H;
@@ -192,7 +235,13 @@ __device__ __noinline__ void gemm_tasks(const StepParams& p, Smem& sm, const Gem
     stage_tile(sm, 0, d.X, d.ldx, 0, Kc, M);
     if (sm.nbuf > 1 && n_chunks > 1) stage_tile(sm, 1, d.X, d.ldx, Kc, Kc, M);
     if (d.lnw != nullptr) {
-      for (int i = threadIdx.x; i < H; i += ST_THREADS) { sm.lnp[i] = d.lnw[i]; sm.lnp[H + i] = d.lnb[i]; }
+      // gamma | beta -> shared (vector loads, all in flight)
+      for (int i = threadIdx.x * 4; i < H; i += ST_THREADS * 4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(d.lnw + i);
+        const float4 b4 = *reinterpret_cast<const float4*>(d.lnb + i);
+        *reinterpret_cast<float4*>(sm.lnp + i) = g4;
+        *reinterpret_cast<float4*>(sm.lnp + H + i) = b4;
+      }
     }
     float acc[2][NT][4];
 #pragma unroll
@@ -213,11 +262,13 @@ __device__ __noinline__ void gemm_tasks(const StepParams& p, Smem& sm, const Gem
         if (sm.nbuf == 1) stage_tile(sm, 0, d.X, d.ldx, c * Kc, Kc, M);
       }
       wait_tile(sm, buf);
+      if (c == 0) prof_mark(sm.prof, 1);
       if (d.lnw != nullptr) {
         __syncthreads();  // lnp visible
         ln_tile(sm.tile[buf], sm.pitch, Kc, M, sm.lnp, H, p.eps);
         __syncthreads();
       }
+      if (c == 0) prof_mark(sm.prof, 2);
       const bf16* xs = sm.tile[buf];
       for (int i0 = 0; i0 < per_chunk; i0 += PF) {
 #pragma unroll
@@ -245,6 +296,7 @@ __device__ __noinline__ void gemm_tasks(const StepParams& p, Smem& sm, const Gem
       }
       if (sm.nbuf > 1 && c + 2 < n_chunks) stage_tile(sm, buf, d.X, d.ldx, (c + 2) * Kc, Kc, M);
     }
+    prof_mark(sm.prof, 3);
     __syncthreads();
     float* red = reinterpret_cast<float*>(sm.scratch);  // [8][32][FB], aliases the (now idle) tile buffers
     {
@@ -275,17 +327,16 @@ __device__ __noinline__ void gemm_tasks(const StepParams& p, Smem& sm, const Gem
       if (d.epi == EPI_F32) reinterpret_cast<float*>(d.Y)[yo] = v;
       else reinterpret_cast<bf16*>(d.Y)[yo] = __float2bfloat16_rn(v);
     }
+    prof_mark(sm.prof, 4);
   }
 }
 
-__device__ __noinline__ void run_gemm(const StepParams& p, Smem& sm, const GemmDesc& d, int nt) {
-  switch (nt) {
+__device__ __forceinline__ void run_gemm(const StepParams& p, Smem& sm, const GemmDesc& d, int nt) {
+  switch (nt) {  // variant set chosen so the fused kernel compiles without register spills (254 regs)
     case 1: gemm_tasks<1, 4>(p, sm, d); break;
     case 2: gemm_tasks<2, 4>(p, sm, d); break;
-    case 3: gemm_tasks<3, 4>(p, sm, d); break;
-    case 4: gemm_tasks<4, 4>(p, sm, d); break;
-    case 6: gemm_tasks<6, 2>(p, sm, d); break;
-    default: gemm_tasks<9, 2>(p, sm, d); break;
+    case 3: gemm_tasks<3, 2>(p, sm, d); break;
+    default: gemm_tasks<4, 2>(p, sm, d); break;
   }
 }
 
@@ -296,14 +347,38 @@ __device__ __forceinline__ void prefetch_slice(const char* w, int N, int K, int 
     l2_prefetch(w + (size_t)task * nt * K * 16, (uint32_t)(nt * K * 16));
 }
 
-// Two attention items per CTA (one per 128-thread half), named barriers 1 and 2.
-__device__ __noinline__ void attn_phase(const StepParams& p, Smem& sm, const AttnArgs& a, int nkv) {
-  const int half = threadIdx.x >> 7, tid = threadIdx.x & 127;
-  float* region = reinterpret_cast<float*>(sm.scratch) + (size_t)half * p.attn_floats_per_half;
+// Attention phase: one warp per (batch row, kv head) item, TMA-staged K/V.  Items are dealt round-robin over
+// CTAs first (item i -> CTA i % grid, warp i / grid) so all 148 SMs pull K/V, 3-4 warps each at Mini/B=32.
+__device__ __forceinline__ void attn_phase(const StepParams& p, Smem& sm, const AttnArgs& a, int nkv, int pos, uint32_t& att_parity) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* region = sm.scratch + (size_t)warp * attn_decode_smem_per_warp<bf16>();
+  uint64_t* bars = sm.bars + 2 + 2 * warp;
   const int items = p.B * nkv;
-  for (int it = blockIdx.x * 2 + half; it < items; it += gridDim.x * 2) {
-    const int b = it / nkv, kvh = it - b * nkv;
-    attention_item<bf16>(a, b, kvh, region, tid, [half] { asm volatile("bar.sync %0, 128;" ::"r"(half + 1) : "memory"); });
+  __syncthreads();  // the tile / reduction scratch of the previous GEMM phase is dead
+  for (int it = blockIdx.x + gridDim.x * warp; it < items; it += gridDim.x * ST_WARPS)
+    attention_decode_item_warp<bf16>(a, it / nkv, it % nkv, pos, region, bars, lane, att_parity);
+}
+
+// L2 prefetch of the K/V rows this CTA's warps will read in the coming attention phases of layer l.
+__device__ __forceinline__ void prefetch_kv(const StepParams& p, int l, int pos) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (pos > 0 && lane == 0) {
+    const char* kc = p.self_kv + p.self_layer_stride * l;
+    const size_t vofs = (size_t)p.B * p.nkv * p.Tmax * HD * 2;
+    for (int it = blockIdx.x + gridDim.x * warp; it < p.B * p.nkv; it += gridDim.x * ST_WARPS) {
+      const char* k = kc + (size_t)it * p.Tmax * HD * 2;  // [B][nkv][Tmax][64]: item-major
+      l2_prefetch(k, (uint32_t)(pos * HD * 2));
+      l2_prefetch(k + vofs, (uint32_t)(pos * HD * 2));
+    }
+  }
+  if (lane == 0) {  // cross K/V of this CTA's items (item-major, contiguous)
+    const char* ck = p.cross_kv + p.cross_layer_stride * l;
+    const size_t vofs = (size_t)p.B * p.nckv * p.S * HD * 2;
+    for (int it = blockIdx.x + gridDim.x * warp; it < p.B * p.nckv; it += gridDim.x * ST_WARPS) {
+      const char* k = ck + (size_t)it * p.S * HD * 2;
+      l2_prefetch(k, (uint32_t)(p.S * HD * 2));
+      l2_prefetch(k + vofs, (uint32_t)(p.S * HD * 2));
+    }
   }
 }
 
@@ -326,25 +401,31 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
 
   Smem sm;
   sm.bars = reinterpret_cast<uint64_t*>(smem_raw);
-  sm.lnp = reinterpret_cast<float*>(smem_raw + 128);
-  sm.scratch = smem_raw + 128 + (size_t)2 * H * sizeof(float);
+  sm.lnp = reinterpret_cast<float*>(smem_raw + 256);
+  sm.scratch = smem_raw + 256 + (size_t)2 * H * sizeof(float);
   sm.pitch = H + 8;
   sm.nbuf = p.nbuf;
   sm.tile[0] = reinterpret_cast<bf16*>(sm.scratch);
   sm.tile[1] = sm.tile[0] + (size_t)32 * sm.pitch;
   sm.parity = 0;
+  sm.prof = nullptr;
   if (tid == 0) {
     mbar_init(&sm.bars[0], 1);
     mbar_init(&sm.bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  attention_decode_init_warp(sm.bars + 2 + 2 * warp, lane);  // per-warp K/V ring barriers: header bytes [16, 144)
+  uint32_t att_parity = 0;
   // rows >= B of the tile buffers are never written by the TMA copies: clear them once
   for (int i = tid; i < (int)(p.tile_region_bytes / 16); i += ST_THREADS) reinterpret_cast<uint4*>(sm.scratch)[i] = make_uint4(0, 0, 0, 0);
-  GridBar bar{p.bar + (gen & 1u), 0u};
+  unsigned* const bar_ctr = p.bar + (gen & 1u);
+  unsigned bar_target = 0u;
   if (blockIdx.x == 0 && tid == 0) p.bar[(gen + 1u) & 1u] = 0u;  // the counter the NEXT launch will use
   __syncthreads();
 
   const char* blob = p.blob;
+  sm.prof = (p.prof != nullptr && blockIdx.x == 0) ? p.prof : nullptr;
+  prof_mark(sm.prof, 0);
   // ---- phase 0: embeddings (one batch row per CTA) + L2 prefetch of layer 0 ----
   if (tid == 0) {
     const char* lb = blob + p.layer0;
@@ -359,28 +440,30 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
     const bf16* tables = reinterpret_cast<const bf16*>(blob + p.embed);
     const bf16* postab = p.rope ? nullptr : reinterpret_cast<const bf16*>(blob + p.pos);
     for (int c = tid; c < H; c += ST_THREADS) {
+      float ev[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++)  // all K gathers in flight, then the left-to-right rounded sum
+        if (k < p.K) ev[k] = __bfloat162float(tables[((size_t)k * (p.V + 1) + p.sa.cur_ids[b * p.K + k]) * H + c]);
       float v = 0.f;
-      for (int k = 0; k < p.K; k++) {
-        const int id = p.sa.cur_ids[b * p.K + k];
-        const float e = __bfloat162float(tables[((size_t)k * (p.V + 1) + id) * H + c]);
-        v = (k == 0) ? e : DT<bf16>::rnd(v + e);
-      }
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+        if (k < p.K) v = (k == 0) ? ev[k] : DT<bf16>::rnd(v + ev[k]);
       if (postab != nullptr) v = DT<bf16>::rnd(v + __bfloat162float(postab[(size_t)pos * H + c]));
       p.x[(size_t)b * H + c] = __float2bfloat16_rn(v);
     }
   }
-  bar.sync();
-
-  AttnArgs at{};
-  at.ldo = H; at.out = p.attn; at.ctrl = nullptr; at.B = p.B; at.nh = p.nh; at.q_len = 1;
-  at.past_from_ctrl = 0; at.past_len = pos; at.prefix = p.P;
-  at.rope = p.rope; at.rope_cos = blob + p.rope_cos; at.rope_sin = blob + p.rope_sin; at.scale = p.scale;
+  prof_mark(sm.prof, 6);
+  bar_target = grid_sync(bar_ctr, bar_target);
+  prof_mark(sm.prof, 7);
 
   // One loop over all 8L+1 dependent phases (single call site per phase type keeps code size and registers sane).
 #pragma unroll 1
   for (int ph = 0; ph <= 8 * p.L; ph++) {
     const int l = ph >> 3, sub = (ph == 8 * p.L) ? 8 : (ph & 7);
+    sm.prof = (p.prof != nullptr && blockIdx.x == 0) ? p.prof + (size_t)(ph + 1) * 8 : nullptr;
+    prof_mark(sm.prof, 0);
     const char* lb = blob + p.layer0 + p.layer_stride * (l < p.L ? l : p.L - 1);
+    if (sub == 0) prefetch_kv(p, l, pos);
     if (sub == 0 && tid == 0) {  // pull the NEXT layer's weight slices (or the lm heads) into L2 while this layer runs
       if (l + 1 < p.L) {
         const char* nb = lb + p.layer_stride;
@@ -395,7 +478,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
       }
     }
     if (sub == 1 || sub == 4) {
-      AttnArgs a = at;
+      AttnArgs a{};
+      a.ldo = H; a.out = p.attn; a.ctrl = nullptr; a.B = p.B; a.nh = p.nh; a.q_len = 1;
+      a.past_from_ctrl = 0; a.past_len = pos; a.prefix = p.P;
+      a.rope = p.rope; a.rope_cos = blob + p.rope_cos; a.rope_sin = blob + p.rope_sin; a.scale = p.scale;
       if (sub == 1) {  // self-attention over the cache (+ append of the new K/V row)
         a.q = p.qkv; a.ldq = p.qkv_rows; a.q_col0 = 0;
         a.knew = p.qkv; a.vnew = p.qkv; a.ldkv = p.qkv_rows; a.k_col0 = p.nh * HD; a.v_col0 = (p.nh + p.nkv) * HD;
@@ -407,12 +493,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
       } else {         // cross-attention over the cached encoder K/V
         a.q = p.qc; a.ldq = H; a.q_col0 = 0; a.knew = nullptr; a.vnew = nullptr;
         char* ck = p.cross_kv + p.cross_layer_stride * l;
-        a.kcache = ck; a.vcache = ck + (size_t)p.nckv * HD * 2;
-        a.kv_b_stride = (int64_t)p.S * p.ckv_rows; a.kv_h_stride = HD; a.kv_t_stride = p.ckv_rows;
+        a.kcache = ck; a.vcache = ck + (size_t)p.B * p.nckv * p.S * HD * 2;
+        a.kv_b_stride = (int64_t)p.nckv * p.S * HD; a.kv_h_stride = (int64_t)p.S * HD; a.kv_t_stride = HD;
         a.key_mask = p.enc_mask; a.mask_len = p.S; a.mask_ld = p.S;
         a.nkv = p.nckv; a.cross = 1; a.kv_len = p.S; a.kv_capacity = p.S;
       }
-      attn_phase(p, sm, a, a.nkv);
+      attn_phase(p, sm, a, a.nkv, pos, att_parity);
     } else {
       GemmDesc g{};
       int nt = p.nt_h;
@@ -448,14 +534,16 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
       }
       run_gemm(p, sm, g, nt);
     }
-    if (ph < 8 * p.L) bar.sync();
+    prof_mark(sm.prof, 6);
+    if (ph < 8 * p.L) bar_target = grid_sync(bar_ctr, bar_target, p.progress, ph + 1);
+    prof_mark(sm.prof, 7);
   }
-  bar.sync();
+  bar_target = grid_sync(bar_ctr, bar_target);
   if (p.do_sample_phase) {
     const ptts_gen_params gp = *p.sa.gen;
     const int BK = p.B * p.K;
     sample_phase<ITEMS>(p.sa, gp, BK, cur_len);
-    bar.sync();
+    bar_target = grid_sync(bar_ctr, bar_target);
   }
   if (blockIdx.x == 0 && tid == 0) {
     if (p.do_sample_phase) {
@@ -471,7 +559,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
 
 // ---- host side ----------------------------------------------------------------------------------
 int step_smem_bytes(const StepParams& p) {
-  return (int)(128 + (size_t)2 * p.H * sizeof(float) + p.tile_region_bytes);
+  return (int)(256 + (size_t)2 * p.H * sizeof(float) + p.tile_region_bytes);
 }
 
 int launch_decode_step(const StepParams& p, int grid, cudaStream_t st) {

@@ -25,10 +25,12 @@ struct StepParams {
   // schedule
   int nt_qkv, nt_h, nt_fc1, nt_heads;
   int nbuf;                // activation-tile buffers (2 = double-buffered K chunks)
-  int attn_floats_per_half;
+  int attn_floats_per_warp;
   int64_t tile_region_bytes;
   int do_sample_phase;     // 1: logits -> token inside the kernel (ptts_decode_steps); 0: stop at the logits
   int sample_items;        // ceil(V / 32)
+  int* progress;           // debug: last phase each CTA arrived at (printed on a barrier timeout)
+  long long* prof;         // optional [(8L+2)][8] clock64 timestamps written by CTA 0 (debug / profiles)
 };
 
 int step_smem_bytes(const StepParams& p);
