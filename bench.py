@@ -126,6 +126,8 @@ def run_reference(args, rank):
     """CPU arm: the oracle port of the reference generate() loop on the host cores (fp32, like configs[0])."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses all physical host cores regardless of the launcher
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
     from oracle.config import mini_cfg
     from oracle.weights import make_decoder_weights
     from oracle.decoder import OracleDecoder
@@ -159,6 +161,7 @@ def run_reference(args, rank):
 
 def cpu_baseline_quick():
     """~10-30 s of CPU work: the oracle port on a bounded sample of the same workload (rank 0, N=1)."""
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
     from oracle.config import mini_cfg
     from oracle.weights import make_decoder_weights
     from oracle.decoder import OracleDecoder

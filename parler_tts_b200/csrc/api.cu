@@ -529,12 +529,15 @@ int ptts_dac_pack(const ptts_dac_config* cfg, void* blob, int32_t name_id, const
   PTTS_REQUIRE(numel == t.numel, "dac pack: tensor %d expects %lld elements, got %lld", name_id, (long long)t.numel, (long long)numel);
   char* dst = (char*)blob + t.off;
   if (t.kind == DK_PLAIN) return pack_plain(src, src_dtype, numel, dst, cfg->dtype, (cudaStream_t)stream);
+  if (t.off_k >= 0) {
+    if (int e = pack_conv_kmajor(src, src_dtype, (char*)blob + t.off_k, t.d0, t.d1, t.k, t.kind == DK_CONVT, (cudaStream_t)stream)) return e;
+  }
   return pack_conv(src, src_dtype, dst, cfg->dtype, t.d0, t.d1, t.k, t.kind == DK_CONVT, (cudaStream_t)stream);
 }
 int ptts_dac_workspace_bytes(const ptts_dac_config* cfg, int32_t B, int32_t T, int64_t* out_bytes) {
   PTTS_REQUIRE(cfg && out_bytes && B > 0 && T > 0, "bad argument");
   if (int e = validate_dac(*cfg)) return e;
-  *out_bytes = 2 * align_up(dac_max_act_per_frame(*cfg) * B * T * dtype_size(cfg->dtype), 256);
+  *out_bytes = 3 * align_up(dac_max_act_per_frame(*cfg) * B * T * dtype_size(cfg->dtype), 1024) + align_up((int64_t)cfg->latent_dim * B * T * dtype_size(cfg->dtype), 1024);
   return PTTS_OK;
 }
 
@@ -545,13 +548,72 @@ int ptts_dac_decode(const ptts_dac_config* cfg, const void* blob, void* workspac
   PTTS_REQUIRE(B > 0 && T > 0, "dac decode: empty input B=%d T=%d", B, T);
   const DacLayout L = make_dac_layout(*cfg);
   const int es = L.es;
-  const int64_t half = align_up(dac_max_act_per_frame(*cfg) * B * T * es, 256);
-  PTTS_REQUIRE(workspace_bytes >= 2 * half, "dac decode: workspace too small");
+  const int64_t half = align_up(dac_max_act_per_frame(*cfg) * B * T * es, 1024);
+  const int64_t zbytes = align_up((int64_t)cfg->latent_dim * B * T * es, 1024);
+  PTTS_REQUIRE(workspace_bytes >= 3 * half + zbytes, "dac decode: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const char* bl = (const char*)blob;
   char* cur = (char*)workspace;
   char* oth = cur + half;
   const int K = cfg->n_codebooks;
+  // ---- tensor-core path: bf16 storage, every conv but the last (Cout = 1) as a tcgen05 implicit GEMM ----
+  bool use_tc = (cfg->dtype == PTTS_BF16) && env_flag("PTTS_DAC_TC", true) && conv_tc_supported(cfg->latent_dim, cfg->decoder_dim);
+  for (int bi = 0; bi < cfg->n_blocks && use_tc; bi++) use_tc = conv_tc_supported(cfg->decoder_dim >> bi, cfg->decoder_dim >> (bi + 1)) && conv_tc_supported(cfg->decoder_dim >> (bi + 1), cfg->decoder_dim >> (bi + 1));
+  if (use_tc) {
+    char* bufA = (char*)workspace;
+    char* bufB = bufA + half;
+    char* bufX = bufB + half;
+    char* bufZ = bufX + half;
+    FromCodesArgs fz{codes, bl + L.codebooks, bl + L.proj_w, bl + L.proj_b, bufZ, K, cfg->codebook_dim, cfg->latent_dim, T, cfg->codebook_size};
+    if (int e = launch_from_codes(fz, cfg->dtype, B, st)) return e;
+    int ti = 3 * K;
+    auto tpk = [&](int i) { return bl + L.t[i].off_k; };
+    auto tpp = [&](int i) { return bl + L.t[i].off; };
+    auto convk = [&](const void* x, int w_i, int b_i, const void* res, void* out_raw, void* out_act, const void* alpha_next, int Cin, int Cout, int Tlen, int ks, int dil) {
+      ConvArgs a{};
+      a.x = x; a.bias = tpp(b_i); a.res = res;
+      a.Cin = Cin; a.Cout = Cout; a.Tin = Tlen; a.Tout = Tlen; a.q_count = Tlen;
+      a.n_taps = ks; a.off_base = -((ks - 1) / 2) * dil; a.off_step = dil; a.wt_base = 0; a.wt_step = 1;
+      a.n_phase = 1; a.wt_phase_step = 0; a.o_mul = 1; a.o_add = 0; a.o_phase_step = 0;
+      return launch_conv_tc(a, tpk(w_i), ks, alpha_next, out_raw, out_act, B, st);
+    };
+    const int C = cfg->decoder_dim;
+    char* act = bufA;   // snake'd input of the next conv
+    char* oth2 = bufB;
+    // conv1: latent -> C, output only as snake_{block0.snake1}(y)
+    if (int e = convk(bufZ, ti, ti + 1, nullptr, nullptr, act, tpp(ti + 2), cfg->latent_dim, C, T, 7, 1)) return e;
+    ti += 2;
+    int Tlen = T;
+    for (int bi = 0; bi < cfg->n_blocks; bi++) {
+      const int cin = C >> bi, cout = C >> (bi + 1), sd = cfg->strides[bi];
+      const int pad = (sd + 1) / 2;
+      ConvArgs a{};
+      a.x = act; a.bias = tpp(ti + 2); a.res = nullptr;
+      a.Cin = cin; a.Cout = cout; a.Tin = Tlen; a.Tout = Tlen * sd; a.q_count = Tlen + 1;
+      a.n_taps = 2; a.off_base = 0; a.off_step = -1; a.wt_base = 0; a.wt_step = sd;
+      a.n_phase = sd; a.wt_phase_step = 1; a.o_mul = sd; a.o_add = -pad; a.o_phase_step = 1;
+      // raw -> X (residual stream of the block), snake_{res1.snake1}(x) -> the other activation buffer
+      if (int e = launch_conv_tc(a, tpk(ti + 1), 2 * sd, tpp(ti + 3), bufX, oth2, B, st)) return e;
+      ti += 3;
+      std::swap(act, oth2);
+      Tlen *= sd;
+      const int dil[3] = {1, 3, 9};
+      for (int r = 0; r < 3; r++) {
+        // y = conv7(snake1(x)) -> only snake2(y) is stored; x += conv1(snake2(y)), plus snake_next(x) for the next unit
+        if (int e = convk(act, ti + 1, ti + 2, nullptr, nullptr, oth2, tpp(ti + 3), cout, cout, Tlen, 7, dil[r])) return e;
+        const int next_alpha = ti + 6;  // next unit's snake1, next block's snake1, or the decoder's final snake1
+        if (int e = convk(oth2, ti + 4, ti + 5, bufX, bufX, act, tpp(next_alpha), cout, cout, Tlen, 1, 1)) return e;
+        ti += 6;
+      }
+    }
+    const int cl = C >> cfg->n_blocks;
+    ConvArgs f{};  // final conv (Cout = 1) + tanh on the already snake'd tensor: generic kernel
+    f.x = act; f.w = tpp(ti + 1); f.bias = tpp(ti + 2); f.alpha = nullptr; f.res = nullptr; f.out = audio_out;
+    f.Cin = cl; f.Cout = 1; f.Tin = Tlen; f.Tout = Tlen; f.q_count = Tlen;
+    f.n_taps = 7; f.off_base = -3; f.off_step = 1; f.wt_base = 0; f.wt_step = 1;
+    f.n_phase = 1; f.wt_phase_step = 0; f.o_mul = 1; f.o_add = 0; f.o_phase_step = 0; f.tanh_out = 1;
+    return launch_conv(f, cfg->dtype, B, st);
+  }
   FromCodesArgs fc{codes, bl + L.codebooks, bl + L.proj_w, bl + L.proj_b, cur, K, cfg->codebook_dim, cfg->latent_dim, T, cfg->codebook_size};
   if (int e = launch_from_codes(fc, cfg->dtype, B, st)) return e;
   int ti = 3 * K;  // tensor cursor (see make_dac_layout order)

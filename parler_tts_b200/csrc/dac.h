@@ -26,6 +26,10 @@ struct FromCodesArgs {
 };
 int launch_from_codes(const FromCodesArgs& a, int dtype, int B, cudaStream_t st);
 int pack_conv(const void* src, int src_dtype, void* dst, int dst_dtype, int d0, int d1, int k, int transposed, cudaStream_t st);
+// tcgen05 path (dac_tc.cu)
+bool conv_tc_supported(int Cin, int Cout);
+int launch_conv_tc(const ConvArgs& a, const void* w_kmajor, int taps_total, const void* alpha_next, void* out_raw, void* out_act, int B, cudaStream_t st);
+int pack_conv_kmajor(const void* src, int src_dtype, void* dst, int d0, int d1, int k, int transposed, cudaStream_t st);
 
 enum { DK_PLAIN = 0, DK_CONV = 1, DK_CONVT = 2 };
 struct DacTensor {
@@ -33,6 +37,7 @@ struct DacTensor {
   int d0, d1, k;   // source dims (conv: co,ci,k; convT: ci,co,k; plain: numel,1,1)
   int64_t off;     // byte offset in blob
   int64_t numel;
+  int64_t off_k;   // conv weights: second copy [tap][Cout][Cin] bf16 for the tcgen05 path (-1: none)
 };
 
 struct DacLayout {
@@ -57,8 +62,9 @@ static inline DacLayout make_dac_layout(const ptts_dac_config& c) {
   L.es = dtype_size(c.dtype);
   int64_t o = 0;
   auto add = [&](int kind, int d0, int d1, int k) {
-    DacTensor t{kind, d0, d1, k, o, (int64_t)d0 * d1 * k};
+    DacTensor t{kind, d0, d1, k, o, (int64_t)d0 * d1 * k, -1};
     o = align_up(o + t.numel * L.es, 256);
+    if (kind != DK_PLAIN && c.dtype == PTTS_BF16) { t.off_k = o; o = align_up(o + t.numel * 2, 1024); }
     L.t.push_back(t);
   };
   const int K = c.n_codebooks, D = c.codebook_dim, Z = c.latent_dim;
@@ -68,9 +74,9 @@ static inline DacLayout make_dac_layout(const ptts_dac_config& c) {
   L.proj_b = L.proj_w + align_up((int64_t)K * Z * D * L.es, 256);
   o = L.proj_b + align_up((int64_t)K * Z * L.es, 256);
   for (int k = 0; k < K; k++) {
-    L.t.push_back({DK_PLAIN, c.codebook_size * D, 1, 1, L.codebooks + (int64_t)k * c.codebook_size * D * L.es, (int64_t)c.codebook_size * D});
-    L.t.push_back({DK_PLAIN, Z * D, 1, 1, L.proj_w + (int64_t)k * Z * D * L.es, (int64_t)Z * D});
-    L.t.push_back({DK_PLAIN, Z, 1, 1, L.proj_b + (int64_t)k * Z * L.es, (int64_t)Z});
+    L.t.push_back({DK_PLAIN, c.codebook_size * D, 1, 1, L.codebooks + (int64_t)k * c.codebook_size * D * L.es, (int64_t)c.codebook_size * D, -1});
+    L.t.push_back({DK_PLAIN, Z * D, 1, 1, L.proj_w + (int64_t)k * Z * D * L.es, (int64_t)Z * D, -1});
+    L.t.push_back({DK_PLAIN, Z, 1, 1, L.proj_b + (int64_t)k * Z * L.es, (int64_t)Z, -1});
   }
   const int C = c.decoder_dim;
   add(DK_CONV, C, Z, 7); add(DK_PLAIN, C, 1, 1);

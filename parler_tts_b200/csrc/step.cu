@@ -430,6 +430,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
   if (tid == 0) {
     const char* lb = blob + p.layer0;
     prefetch_slice(lb + p.wqkv, p.qkv_rows, H, p.nt_qkv);
+    l2_prefetch(lb + p.ln1_w, (uint32_t)H * 4); l2_prefetch(lb + p.ln1_b, (uint32_t)H * 4);
+    l2_prefetch(lb + p.ln2_w, (uint32_t)H * 4); l2_prefetch(lb + p.ln2_b, (uint32_t)H * 4);
+    l2_prefetch(lb + p.ln3_w, (uint32_t)H * 4); l2_prefetch(lb + p.ln3_b, (uint32_t)H * 4);
     prefetch_slice(lb + p.wo, H, H, p.nt_h);
     prefetch_slice(lb + p.wqc, H, H, p.nt_h);
     prefetch_slice(lb + p.woc, H, H, p.nt_h);
@@ -464,17 +467,24 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
     prof_mark(sm.prof, 0);
     const char* lb = blob + p.layer0 + p.layer_stride * (l < p.L ? l : p.L - 1);
     if (sub == 0) prefetch_kv(p, l, pos);
-    if (sub == 0 && tid == 0) {  // pull the NEXT layer's weight slices (or the lm heads) into L2 while this layer runs
-      if (l + 1 < p.L) {
-        const char* nb = lb + p.layer_stride;
-        prefetch_slice(nb + p.wqkv, p.qkv_rows, H, p.nt_qkv);
-        prefetch_slice(nb + p.wo, H, H, p.nt_h);
-        prefetch_slice(nb + p.wqc, H, H, p.nt_h);
-        prefetch_slice(nb + p.woc, H, H, p.nt_h);
-        prefetch_slice(nb + p.fc1, p.F, H, p.nt_fc1);
-        prefetch_slice(nb + p.fc2, H, p.F, p.nt_h);
-      } else {
-        prefetch_slice(blob + p.heads, p.K * p.V, H, p.nt_heads);
+    if (tid == 0) {
+      // Pull the NEXT layer's weights into L2 while this layer runs, one matrix per phase (the matrix phase `sub`
+      // of the next layer will use), so the HBM stream is spread over the layer instead of colliding with one
+      // phase's activation staging.  LayerNorm parameters ride along (they would otherwise be cold HBM reads
+      // on the critical path of every LN-fused GEMM).
+      const bool last = (l + 1 >= p.L);
+      const char* nb = lb + p.layer_stride;
+      switch (sub) {
+        case 0:
+          if (!last) { prefetch_slice(nb + p.wqkv, p.qkv_rows, H, p.nt_qkv); l2_prefetch(nb + p.ln1_w, (uint32_t)H * 4); l2_prefetch(nb + p.ln1_b, (uint32_t)H * 4); }
+          else { prefetch_slice(blob + p.heads, p.K * p.V, H, p.nt_heads); l2_prefetch(blob + p.final_ln_w, (uint32_t)H * 4); l2_prefetch(blob + p.final_ln_b, (uint32_t)H * 4); }
+          break;
+        case 2: if (!last) prefetch_slice(nb + p.wo, H, H, p.nt_h); break;
+        case 3: if (!last) { prefetch_slice(nb + p.wqc, H, H, p.nt_h); l2_prefetch(nb + p.ln2_w, (uint32_t)H * 4); l2_prefetch(nb + p.ln2_b, (uint32_t)H * 4); } break;
+        case 5: if (!last) prefetch_slice(nb + p.woc, H, H, p.nt_h); break;
+        case 6: if (!last) { prefetch_slice(nb + p.fc1, p.F, H, p.nt_fc1); l2_prefetch(nb + p.ln3_w, (uint32_t)H * 4); l2_prefetch(nb + p.ln3_b, (uint32_t)H * 4); } break;
+        case 7: if (!last) prefetch_slice(nb + p.fc2, H, p.F, p.nt_h); break;
+        default: break;
       }
     }
     if (sub == 1 || sub == 4) {

@@ -490,3 +490,24 @@ def test_fused_step_mini_shape_batch32(monkeypatch):
     b_ids, b_log, _ = _free_run_bf16(cfg, w, 32, 16, 8, 22, False, monkeypatch)
     assert np.array_equal(a_ids, b_ids)
     assert np.array_equal(a_log, b_log)
+
+
+def test_dac_decode_real_shape_bf16_tensor_core(monkeypatch):
+    """44.1 kHz DAC shape in bf16: the tcgen05 implicit-GEMM path vs the fp32 oracle (and vs the SIMT bf16 path)."""
+    from parler_tts_b200 import DACModel
+    from tests.helpers import product_dac_config
+    dcfg = dac_cfg()
+    w = make_dac_weights(dcfg, seed=3)
+    g = torch.Generator().manual_seed(9)
+    codes = torch.randint(0, 1024, (2, 9, 5), generator=g)
+    ref = OracleDAC(dcfg, w).decode(codes[None]).numpy()
+    outs = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("PTTS_DAC_TC", tc)
+        m = DACModel(product_dac_config(dcfg), DEV, torch.bfloat16).load_state_dict(w)
+        outs[tc] = m.decode(codes[None].to(DEV), [None]).audio_values.float().cpu().numpy()
+        assert outs[tc].shape == ref.shape
+    e_tc, e_simt = rms(outs["1"] - ref), rms(outs["0"] - ref)
+    # bf16 storage between layers dominates both; the tensor-core path must be no worse than the FMA path
+    assert e_tc < 0.1 * rms(ref) + 1e-3, (e_tc, rms(ref))
+    assert e_tc < 1.5 * e_simt + 1e-3, (e_tc, e_simt)
