@@ -106,6 +106,34 @@ def synthetic_state_dict(cfg, device, seed=0):
     return sd
 
 
+def synth_dac_weights(cfg, device):
+    import math
+    g = torch.Generator(device=device).manual_seed(0)
+    sd = {}
+    C = cfg.decoder_dim
+    def rn(*s, scale=1.0): return torch.randn(*s, generator=g, device=device) * scale
+    for i in range(cfg.num_codebooks):
+        sd[f"quantizer.quantizers.{i}.codebook.weight"] = rn(cfg.codebook_size, cfg.codebook_dim)
+        sd[f"quantizer.quantizers.{i}.out_proj.weight"] = rn(cfg.latent_dim, cfg.codebook_dim, 1, scale=1 / math.sqrt(8 * 9))
+        sd[f"quantizer.quantizers.{i}.out_proj.bias"] = rn(cfg.latent_dim, scale=0.02)
+    sd["decoder.conv1.weight"] = rn(C, cfg.latent_dim, 7, scale=1 / math.sqrt(7 * cfg.latent_dim)); sd["decoder.conv1.bias"] = rn(C, scale=0.02)
+    for bi, s in enumerate(cfg.decoder_rates):
+        cin, cout = C >> bi, C >> (bi + 1)
+        p = f"decoder.block.{bi}."
+        sd[p + "snake1.alpha"] = torch.ones(1, cin, 1, device=device)
+        sd[p + "conv_t1.weight"] = rn(cin, cout, 2 * s, scale=1 / math.sqrt(2 * cin)); sd[p + "conv_t1.bias"] = rn(cout, scale=0.02)
+        for r in (1, 2, 3):
+            u = p + f"res_unit{r}."
+            sd[u + "snake1.alpha"] = torch.ones(1, cout, 1, device=device)
+            sd[u + "conv1.weight"] = rn(cout, cout, 7, scale=0.5 / math.sqrt(7 * cout)); sd[u + "conv1.bias"] = rn(cout, scale=0.02)
+            sd[u + "snake2.alpha"] = torch.ones(1, cout, 1, device=device)
+            sd[u + "conv2.weight"] = rn(cout, cout, 1, scale=0.5 / math.sqrt(cout)); sd[u + "conv2.bias"] = rn(cout, scale=0.02)
+    cl = C >> len(cfg.decoder_rates)
+    sd["decoder.snake1.alpha"] = torch.ones(1, cl, 1, device=device)
+    sd["decoder.conv2.weight"] = rn(1, cl, 7, scale=1 / math.sqrt(7 * cl)); sd["decoder.conv2.bias"] = rn(1, scale=0.02)
+    return sd
+
+
 def synthetic_inputs(B, H, seed, device="cpu", pin=False):
     g = torch.Generator().manual_seed(seed)
     enc_mask = torch.ones(B, S_LEN, dtype=torch.long)
@@ -187,6 +215,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dac", action="store_true")
     ap.add_argument("--decode-steps", type=int, default=DECODE_STEPS)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -287,6 +316,26 @@ def main():
     hbm_peak, peak_src = peaks()
     achieved = byts / (dec_ms * 1e-3) / 1e9
 
+    # DAC decode of the generated frames (reported separately: the metric is the token loop)
+    dac_info = None
+    if rank == 0 and not args.no_dac:
+        model.audio_encoder.load_state_dict(synth_dac_weights(cfg.audio_encoder, dev))
+        frames = L - K
+        codes = torch.randint(0, 1024, (1, B, K, frames), device=dev)
+        for _ in range(2):
+            model.audio_encoder.decode(codes, [None] * B)
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(3):
+            wav = model.audio_encoder.decode(codes, [None] * B).audio_values
+        d1.record()
+        torch.cuda.synchronize()
+        dms = d0.elapsed_time(d1) / 3
+        flops = 1.608e9 * B * frames
+        dac_info = {"ms": dms, "frames": frames, "batch": B, "tflops": flops / dms / 1e9, "audio_seconds": B * frames * 512 / 44100,
+                    "rtf": (B * frames * 512 / 44100) / (dms / 1e3), "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, bf16 in / f32 TMEM accumulate)",
+                    "flop_per_frame": 1.608e9}
     if rank == 0:
         tokens = world * B * K * n_dec * args.steps
         value = tokens / (ms * 1e-3)
@@ -307,9 +356,11 @@ def main():
                            "token matrix read back to host"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "decode step (CUDA graph: embed + 24 x 8 layer kernels + heads + sample)",
+                         "traffic": None, "peak_source": peak_src, "kernel": "decode_step_kernel (one persistent cooperative kernel per token: embed + 24 x 8 phases + heads + sample)",
                          "ms_per_decode_step": dec_ms / n_timed, "algorithmic_bytes_per_step_avg": byts / n_timed},
         }
+        if dac_info is not None:
+            line["dac_decode"] = dac_info
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline_quick()

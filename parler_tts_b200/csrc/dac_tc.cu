@@ -26,7 +26,7 @@ namespace ptts {
 
 constexpr int TC_M = 128;      // time rows per tile (UMMA M)
 constexpr int TC_K = 64;       // ci per pipeline stage (one 128-byte swizzle row of bf16)
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 2;   // 2 stages x <= 48 KB: two CTAs per SM, so one tile's epilogue overlaps the other's MMA mainloop
 constexpr int TC_THREADS = 192;
 
 __device__ __forceinline__ uint32_t tc_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -75,7 +75,7 @@ struct ConvTcArgs {
   const bf16* alpha_next;  // [Cout]
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvTcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,6 +86,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   uint64_t* empty = full + TC_STAGES;
   uint64_t* acc_full = empty + TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  bf16* chan = reinterpret_cast<bf16*>(smem + TC_STAGES * stage_bytes + 128);  // [3][n_tile]: bias | alpha | 1/(alpha+1e-9)
 
   const int phase = blockIdx.z % p.n_phase, b = blockIdx.z / p.n_phase;
   const int q0 = blockIdx.x * TC_M, n0 = blockIdx.y * p.n_tile;
@@ -141,6 +142,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    // per-channel constants of this N tile -> shared memory while the mainloop runs: bias, alpha, 1/(alpha+1e-9)
+    {
+      const int et = threadIdx.x - 64;  // 0..127
+      for (int c = et; c < p.n_tile; c += 128) {
+        chan[c] = p.bias[n0 + c];
+        if (p.out_act != nullptr) {
+          const bf16 a = p.alpha_next[n0 + c];
+          chan[p.n_tile + c] = a;
+          chan[2 * p.n_tile + c] = __float2bfloat16_rn(1.0f / __bfloat162float(__float2bfloat16_rn(__bfloat162float(a) + 1e-9f)));
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+    }
     tc_mbar_wait(acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;
@@ -149,44 +163,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int to = q * p.o_mul + p.o_add + phase * p.o_phase_step;
     const bool row_ok = (q < p.q_count) && (to >= 0) && (to < p.Tout);
     const size_t orow = ((size_t)b * p.Tout + (row_ok ? to : 0)) * p.Cout + n0;
+    const __nv_bfloat162* bias2 = reinterpret_cast<const __nv_bfloat162*>(chan);
+    const __nv_bfloat162* alpha2 = reinterpret_cast<const __nv_bfloat162*>(chan + p.n_tile);
+    const __nv_bfloat162* inv2 = reinterpret_cast<const __nv_bfloat162*>(chan + 2 * p.n_tile);
     for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);  // warp-collective: all lanes take part
       if (row_ok) {
-        float r[32];
+        // native bf16x2 arithmetic: every op rounds to bf16 exactly like the torch ops it replaces
+        __nv_bfloat162 r2[16];
 #pragma unroll
-        for (int i = 0; i < 32; i++) r[i] = DT<bf16>::rnd(__uint_as_float(v[i]) + __bfloat162float(p.bias[n0 + c0 + i]));
+        for (int i = 0; i < 16; i++) {
+          // conv output = bf16(acc + bias) (one rounding of the fp32 sum)
+          const float2 bb = __bfloat1622float2(bias2[(c0 >> 1) + i]);
+          r2[i] = __floats2bfloat162_rn(__uint_as_float(v[2 * i]) + bb.x, __uint_as_float(v[2 * i + 1]) + bb.y);
+        }
         if (p.res != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            float f[8];
-            load8(p.res + orow + c0 + i, f);
+          for (int i = 0; i < 16; i += 4) {
+            const uint4 u = *reinterpret_cast<const uint4*>(p.res + orow + c0 + 2 * i);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-            for (int e = 0; e < 8; e++) r[i + e] = DT<bf16>::rnd(f[e] + r[i + e]);
+            for (int e = 0; e < 4; e++) r2[i + e] = __hadd2(h[e], r2[i + e]);
           }
         }
         if (p.out_raw != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) f[e] = r[i + e];
-            store8(p.out_raw + orow + c0 + i, f);
-          }
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<uint4*>(p.out_raw + orow + c0 + 2 * i) = *reinterpret_cast<const uint4*>(&r2[i]);
         }
         if (p.out_act != nullptr) {
+          __nv_bfloat162 s2[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-              const float a = __bfloat162float(p.alpha_next[n0 + c0 + i + e]);
-              const float inv = DT<bf16>::rnd(1.0f / DT<bf16>::rnd(a + 1e-9f));
-              const float sn = DT<bf16>::rnd(sinf(DT<bf16>::rnd(a * r[i + e])));
-              f[e] = DT<bf16>::rnd(r[i + e] + DT<bf16>::rnd(inv * DT<bf16>::rnd(sn * sn)));
-            }
-            store8(p.out_act + orow + c0 + i, f);
+          for (int i = 0; i < 16; i++) {
+            const __nv_bfloat162 ax = __hmul2(alpha2[(c0 >> 1) + i], r2[i]);          // alpha * x
+            const float2 axf = __bfloat1622float2(ax);
+            const __nv_bfloat162 sn = __floats2bfloat162_rn(__sinf(axf.x), __sinf(axf.y));  // sin(.)  (MUFU; bf16 result)
+            const __nv_bfloat162 sq = __hmul2(sn, sn);                                  // ^2
+            s2[i] = __hadd2(r2[i], __hmul2(inv2[(c0 >> 1) + i], sq));                   // x + inv * sin^2
           }
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<uint4*>(p.out_act + orow + c0 + 2 * i) = *reinterpret_cast<const uint4*>(&s2[i]);
         }
       }
     }
@@ -250,10 +266,10 @@ int launch_conv_tc(const ConvArgs& a, const void* w_kmajor, int taps_total, cons
   if (int e = make_map(&mx, a.x, (uint64_t)a.Cin, (uint64_t)a.Tin, (uint64_t)B, TC_M)) return e;
   if (int e = make_map(&mw, w_kmajor, (uint64_t)a.Cin, (uint64_t)a.Cout, (uint64_t)taps_total, (uint32_t)p.n_tile)) return e;
   const int stage_bytes = (TC_M * TC_K * 2 + p.n_tile * TC_K * 2 + 1023) & ~1023;
-  const size_t smem = (size_t)TC_STAGES * stage_bytes + 128;
+  const size_t smem = (size_t)TC_STAGES * stage_bytes + 128 + 3 * 256 * 2;
   static bool attr = false;
   if (!attr) {
-    PTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    PTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     attr = true;
   }
   dim3 grid((a.q_count + TC_M - 1) / TC_M, a.Cout / p.n_tile, B * a.n_phase);
