@@ -237,7 +237,7 @@ static bool setup_fused(ptts_session* s) {
   int kvcap = W.Tmax > W.S ? W.Tmax : W.S;
   (void)kvcap;
   p.attn_floats_per_warp = 0;
-  const int64_t att = (int64_t)8 * (2 * 2 * 32 * 64 * 2 + 3 * 64 * 4);  // 8 x attn_decode_smem_per_warp<bf16>()
+  const int64_t att = (int64_t)8 * (2 * 2 * 32 * 64 * 2 + 3 * 64 * 4) + 4 * 128 * 4;  // 8 x attn_decode_smem_per_warp<bf16>() + pair exchange
   const int64_t budget = 200 * 1024 - 256 - (int64_t)2 * L.H * 4;
   p.nbuf = (2 * tile <= budget) ? 2 : 1;
   int64_t region = p.nbuf * tile;

@@ -36,17 +36,19 @@ __global__ void __launch_bounds__(256) attention_decode_kernel(AttnArgs p) {
   pdl_launch_dependents();
   pdl_wait();
   if (p.ctrl != nullptr && p.ctrl->active == 0) return;
-  const int it = blockIdx.x * 8 + warp;
+  const int pair = warp >> 1, part = warp & 1;   // two warps per item (they split the cached keys)
+  const int it = blockIdx.x * 4 + pair;
   if (it >= p.B * p.nkv) return;
   int past = p.past_len;
   if (p.past_from_ctrl) past = p.prefix + p.ctrl->cur_len - 1;
   uint32_t parity = 0;
-  attention_decode_item_warp<T>(p, it / p.nkv, it % p.nkv, past, sm_warp, bars, lane, parity);
+  float* xch = reinterpret_cast<float*>(smd + 128 + (size_t)8 * attn_decode_smem_per_warp<T>()) + pair * 128;
+  attention_decode_item_warp<T>(p, it / p.nkv, it % p.nkv, past, sm_warp, bars, lane, parity, part, 2, xch, pair + 1);
 }
 
 int launch_attention(const AttnArgs& a, int dtype, cudaStream_t st, bool pdl) {
   if (a.q_len == 1) {
-    const size_t smem_d = 128 + (size_t)8 * (dtype == PTTS_BF16 ? attn_decode_smem_per_warp<bf16>() : attn_decode_smem_per_warp<float>());
+    const size_t smem_d = 128 + (size_t)8 * (dtype == PTTS_BF16 ? attn_decode_smem_per_warp<bf16>() : attn_decode_smem_per_warp<float>()) + 4 * 128 * sizeof(float);
     static bool attr_d = false;
     if (!attr_d) {
       PTTS_CHECK_CUDA(cudaFuncSetAttribute(attention_decode_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -54,7 +56,7 @@ int launch_attention(const AttnArgs& a, int dtype, cudaStream_t st, bool pdl) {
       attr_d = true;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((a.B * a.nkv + 7) / 8);
+    cfg.gridDim = dim3((a.B * a.nkv + 3) / 4);
     cfg.blockDim = dim3(256);
     cfg.dynamicSmemBytes = smem_d;
     cfg.stream = st;

@@ -207,7 +207,10 @@ __host__ __device__ constexpr int attn_decode_smem_per_warp() {
 
 template <typename T>
 __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, int b, int kvh, int pos, unsigned char* sm_warp, uint64_t* bars,
-                                                           int lane, uint32_t& parity) {
+                                                           int lane, uint32_t& parity, int part = 0, int nparts = 1, float* xch = nullptr,
+                                                           int pair_bar = 0) {
+  // part / nparts: the item's cached keys are split between `nparts` warps (chunk c belongs to warp c % nparts);
+  // partial (max, sum, accumulator) triples are merged through `xch` with a 64-thread named barrier `pair_bar`.
   constexpr int CH = AttChunk<T>::CH;
   constexpr int STAGE_ELEMS = CH * HD;  // per K (or V) stage
   T* kst = reinterpret_cast<T*>(sm_warp);                   // [2][CH][64]
@@ -224,11 +227,12 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
   T* vc = reinterpret_cast<T*>(p.vcache) + (size_t)b * p.kv_b_stride + (size_t)kvh * p.kv_h_stride;
   const int lo = lane, hi = lane + HD / 2;
   const int n_cached = p.cross ? p.kv_len : pos;  // keys that come from the cache
-  const int n_chunks = (n_cached + CH - 1) / CH;
+  const int n_chunks_all = (n_cached + CH - 1) / CH;
+  const int n_chunks = (n_chunks_all > part) ? (n_chunks_all - part + nparts - 1) / nparts : 0;  // chunks of THIS warp
 
-  auto issue = [&](int chunk) {  // TMA: cached rows [chunk*CH, ...) -> stage chunk&1
-    const int st = chunk & 1;
-    const int t0 = chunk * CH;
+  auto issue = [&](int i) {  // TMA: this warp's i-th chunk -> stage i&1
+    const int st = i & 1;
+    const int t0 = (part + nparts * i) * CH;
     const int n = (n_cached - t0 < CH) ? (n_cached - t0) : CH;
     const uint32_t bar = att_smem_u32(&bars[st]);
     if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * n * HD * sizeof(T))) : "memory");
@@ -257,7 +261,7 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
   if (n_chunks > 0) issue(0);
   if (n_chunks > 1) issue(1);
 
-  if (!p.cross) {  // this step's K (rotary applied) and V: to the cache (for later steps) and to shared memory (for now)
+  if (!p.cross && part == 0) {  // this step's K (rotary applied) and V: to the cache (for later steps) and to shared memory (for now)
     const T* ksrc = reinterpret_cast<const T*>(p.knew) + (size_t)b * p.ldkv + p.k_col0 + kvh * HD;
     const T* vsrc = reinterpret_cast<const T*>(p.vnew) + (size_t)b * p.ldkv + p.v_col0 + kvh * HD;
     float x0 = DT<T>::to_f(ksrc[lo]), x1 = DT<T>::to_f(ksrc[hi]);
@@ -365,7 +369,7 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
     for (int c = 0; c < n_chunks; c++) {
       const int st = c & 1;
       wait_stage(st);
-      const int t0 = c * CH;
+      const int t0 = (part + nparts * c) * CH;
       const int n = (n_cached - t0 < CH) ? (n_cached - t0) : CH;
       process(kst + st * STAGE_ELEMS, vst + st * STAGE_ELEMS, t0, n);
       if (c + 2 < n_chunks) {
@@ -374,7 +378,7 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
         issue(c + 2);
       }
     }
-    if (!p.cross) {  // the step's own key (position `pos`), held in shared memory as fp32
+    if (!p.cross && part == 0) {  // the step's own key (position `pos`), held in shared memory as fp32
       __syncwarp();
       float s = 0.f;
       if (grp == 0) {
@@ -402,7 +406,29 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
       acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
       acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
     }
-    if (lane < 8) {
+    if (nparts == 2) {  // merge the two warps' partial softmax states (fixed order: part 0 then part 1)
+      if (part == 1) {
+        if (lane < 8) {
+#pragma unroll
+          for (int e = 0; e < 8; e++) xch[d0 + e] = acc[e];
+        }
+        if (lane == 0) { xch[HD] = m_run; xch[HD + 1] = l_run; }
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      if (part == 0) {
+        const float m1 = xch[HD], l1 = xch[HD + 1];
+        const float mm = fmaxf(m_run, m1);
+        const float c0 = (m_run == -INFINITY) ? 0.f : expf(m_run - mm);
+        const float c1 = (m1 == -INFINITY) ? 0.f : expf(m1 - mm);
+        l_run = l_run * c0 + l1 * c1;
+        if (lane < 8) {
+#pragma unroll
+          for (int e = 0; e < 8; e++) acc[e] = acc[e] * c0 + xch[d0 + e] * c1;
+        }
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    }
+    if (lane < 8 && part == 0) {
       float o[8];
       const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;  // fully masked row -> zeros (never consumed)
 #pragma unroll

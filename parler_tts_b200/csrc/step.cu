@@ -354,9 +354,11 @@ __device__ __forceinline__ void attn_phase(const StepParams& p, Smem& sm, const 
   unsigned char* region = sm.scratch + (size_t)warp * attn_decode_smem_per_warp<bf16>();
   uint64_t* bars = sm.bars + 2 + 2 * warp;
   const int items = p.B * nkv;
+  const int pair = warp >> 1, part = warp & 1;  // two warps per item split its cached keys
+  float* xch = reinterpret_cast<float*>(sm.scratch + (size_t)ST_WARPS * attn_decode_smem_per_warp<bf16>()) + pair * 128;
   __syncthreads();  // the tile / reduction scratch of the previous GEMM phase is dead
-  for (int it = blockIdx.x + gridDim.x * warp; it < items; it += gridDim.x * ST_WARPS)
-    attention_decode_item_warp<bf16>(a, it / nkv, it % nkv, pos, region, bars, lane, att_parity);
+  for (int it = blockIdx.x + gridDim.x * pair; it < items; it += gridDim.x * (ST_WARPS / 2))
+    attention_decode_item_warp<bf16>(a, it / nkv, it % nkv, pos, region, bars, lane, att_parity, part, 2, xch, pair + 1);
 }
 
 // L2 prefetch of the K/V rows this CTA's warps will read in the coming attention phases of layer l.
@@ -365,7 +367,7 @@ __device__ __forceinline__ void prefetch_kv(const StepParams& p, int l, int pos)
   if (pos > 0 && lane == 0) {
     const char* kc = p.self_kv + p.self_layer_stride * l;
     const size_t vofs = (size_t)p.B * p.nkv * p.Tmax * HD * 2;
-    for (int it = blockIdx.x + gridDim.x * warp; it < p.B * p.nkv; it += gridDim.x * ST_WARPS) {
+    for (int it = blockIdx.x + gridDim.x * warp; it < p.B * p.nkv; it += gridDim.x * ST_WARPS) {  // (any warp may prefetch any item)
       const char* k = kc + (size_t)it * p.Tmax * HD * 2;  // [B][nkv][Tmax][64]: item-major
       l2_prefetch(k, (uint32_t)(pos * HD * 2));
       l2_prefetch(k + vofs, (uint32_t)(pos * HD * 2));

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { echo "== $1"; shift; timeout -s KILL "$@" 2>&1 | tail -8; }
+run "ubench" 60 ./tools/ubench_bin
+run "attention-related tests" 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -p no:cacheprovider -k "teacher or fused or greedy or eos or mini" --timeout 100
+echo "== phase profile"; timeout -s KILL 120 python tools/profile_step.py 100 2>&1 | tail -13 | tee gpurun_out/step_phases.txt

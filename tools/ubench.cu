@@ -51,10 +51,14 @@ __global__ void __launch_bounds__(256, 1) k_stage(const bf16* X, bf16* Xpriv, un
   long long tot = 0, tbar = 0;
   const bf16* src = (variant == 4) ? Xpriv + (size_t)blockIdx.x * 32 * 1024 : X;
   for (int it = 0; it < reps; it++) {
+    if (variant >= 5 && blockIdx.x < 128) {  // every CTA rewrites its 8-column slice of all 32 rows, like the GEMM epilogue
+      const int r = tid >> 3, c = tid & 7;
+      const_cast<bf16*>(X)[(size_t)r * 1024 + blockIdx.x * 8 + c] = __float2bfloat16((float)(it + r + c));
+    }
     long long b0 = clock64();
     target = grid_sync(ctr, target, barmode);
     long long t0 = clock64();
-    if (variant == 0 || variant == 1 || variant == 4) {
+    if (variant == 0 || variant == 1 || variant == 4 || variant == 5) {
       if (tid < 32) {
         asm volatile("fence.proxy.async;" ::: "memory");
         if (tid == 0) mbar_expect_tx(bar, 32 * 1024 * 2);
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(256, 1) k_stage(const bf16* X, bf16* Xpriv, un
         }
       }
       mbar_wait(bar, parity); parity ^= 1;
-    } else if (variant == 2) {
+    } else if (variant == 2 || variant == 7) {
       for (int v = tid; v < 32 * 128; v += 256) {
         const int r = v >> 7, c = v & 127;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(tile + r * pitch + c * 8)), "l"(src + (size_t)r * 1024 + c * 8));
@@ -183,8 +187,8 @@ int main() {
     char nm[64]; snprintf(nm, 64, "grid barrier mode %d", mode);
     report(nm, res, grid, 1);
   }
-  const char* vn[5] = {"stage: bulk row (same tile, all CTAs)", "stage: bulk 4 seg staggered", "stage: cp.async 16B", "stage: LDG.128 x16 -> STS", "stage: bulk row, private tile per CTA"};
-  for (int v = 0; v < 5; v++) {
+  const char* vn[8] = {"stage: bulk row (same tile, all CTAs)", "stage: bulk 4 seg staggered", "stage: cp.async 16B", "stage: LDG.128 x16 -> STS", "stage: bulk row, private tile per CTA", "stage: bulk row, tile REWRITTEN by 128 CTAs each round", "stage: LDG.128, tile rewritten each round", "stage: cp.async, tile rewritten each round"};
+  for (int v = 0; v < 8; v++) {
     CK(cudaMemset(ctr, 0, 256));
     int barmode = 0;
     void* args[] = {&X, &Xp, &ctr, &res, &v, &reps, &barmode};
