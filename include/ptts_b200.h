@@ -100,6 +100,11 @@ int ptts_decoder_blob_bytes(const ptts_decoder_config* cfg, int64_t* out_bytes);
 int ptts_decoder_pack(const ptts_decoder_config* cfg, void* blob, int32_t tensor_id, int32_t index,
                       const void* src, int32_t src_dtype, int64_t rows, int64_t cols, void* stream);
 
+/* Call once after every tensor has been packed (bf16 model dtype): folds each LayerNorm's affine part into the
+ * linear layer that follows it (W' = gamma*W, c1 = rowsum(W'), c2 = W*beta), so that the run-time GEMM consumes the
+ * raw residual stream and only needs per-row (mean, rstd).  No-op for f32. */
+int ptts_decoder_finalize(const ptts_decoder_config* cfg, void* blob, void* stream);
+
 /* ---- decoder: generation session ----------------------------------------------------------- */
 /* Workspace bytes for a batch of B utterances, prompt prefix length P, encoder length S and a
  * self-attention cache of max_cache_len positions (>= P + max_length - 1). */

@@ -115,6 +115,26 @@ int ptts_decoder_pack(const ptts_decoder_config* cfg, void* blob, int32_t tensor
   }
 }
 
+int ptts_decoder_finalize(const ptts_decoder_config* cfg, void* blob, void* stream) {
+  PTTS_REQUIRE(cfg && blob, "null argument");
+  if (int e = validate_config(*cfg)) return e;
+  if (cfg->dtype != PTTS_BF16) return PTTS_OK;  // the f32 path applies LayerNorm explicitly
+  const DecoderLayout L = make_layout(*cfg);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* b = (char*)blob;
+  for (int i = 0; i < L.L; i++) {
+    char* lb = b + L.layer0 + L.layer_stride * i;
+    float* cq = (float*)(lb + L.c_qkv);
+    if (int e = fold_layernorm(lb + L.wqkv, L.qkv_rows, L.H, (const float*)(lb + L.ln1_w), (const float*)(lb + L.ln1_b), cq, cq + L.qkv_rows, st)) return e;
+    float* cc = (float*)(lb + L.c_qc);
+    if (int e = fold_layernorm(lb + L.wqc, L.H, L.H, (const float*)(lb + L.ln2_w), (const float*)(lb + L.ln2_b), cc, cc + L.H, st)) return e;
+    float* cf = (float*)(lb + L.c_fc1);
+    if (int e = fold_layernorm(lb + L.fc1, L.F, L.H, (const float*)(lb + L.ln3_w), (const float*)(lb + L.ln3_b), cf, cf + L.F, st)) return e;
+  }
+  float* ch = (float*)(b + L.c_heads);
+  return fold_layernorm(b + L.heads, L.K * L.V, L.H, (const float*)(b + L.final_ln_w), (const float*)(b + L.final_ln_b), ch, ch + L.K * L.V, st);
+}
+
 int ptts_workspace_bytes(const ptts_decoder_config* cfg, int32_t B, int32_t P, int32_t S, int32_t max_cache_len, int64_t* out_bytes) {
   PTTS_REQUIRE(cfg && out_bytes, "null argument");
   if (int e = validate_config(*cfg)) return e;
@@ -212,6 +232,7 @@ static bool setup_fused(ptts_session* s) {
   p.embed = L.embed; p.pos = L.pos; p.layer0 = L.layer0; p.layer_stride = L.layer_stride;
   p.ln1_w = L.ln1_w; p.ln1_b = L.ln1_b; p.wqkv = L.wqkv; p.wo = L.wo; p.ln2_w = L.ln2_w; p.ln2_b = L.ln2_b; p.wqc = L.wqc; p.woc = L.woc;
   p.ln3_w = L.ln3_w; p.ln3_b = L.ln3_b; p.fc1 = L.fc1; p.fc2 = L.fc2;
+  p.c_qkv = L.c_qkv; p.c_qc = L.c_qc; p.c_fc1 = L.c_fc1; p.c_heads = L.c_heads;
   p.final_ln_w = L.final_ln_w; p.final_ln_b = L.final_ln_b; p.heads = L.heads; p.rope_cos = L.rope_cos; p.rope_sin = L.rope_sin;
   char* ws = s->ws;
   p.x = (bf16*)(ws + W.x); p.qkv = (bf16*)(ws + W.qkv); p.attn = (bf16*)(ws + W.attn); p.qc = (bf16*)(ws + W.qc); p.hbuf = (bf16*)(ws + W.hbuf);
@@ -238,7 +259,7 @@ static bool setup_fused(ptts_session* s) {
   (void)kvcap;
   p.attn_floats_per_warp = 0;
   const int64_t att = (int64_t)8 * (2 * 2 * 32 * 64 * 2 + 3 * 64 * 4) + 4 * 128 * 4;  // 8 x attn_decode_smem_per_warp<bf16>() + pair exchange
-  const int64_t budget = 200 * 1024 - 256 - (int64_t)2 * L.H * 4;
+  const int64_t budget = 215 * 1024 - 512;
   p.nbuf = (2 * tile <= budget) ? 2 : 1;
   int64_t region = p.nbuf * tile;
   if (red > region) region = red;
@@ -296,10 +317,13 @@ static int run_forward(ptts_session* s, cudaStream_t st, bool prefill, const voi
   s->launches++;
 
   auto lin = [&](const void* X, int64_t ldx, int64_t woff, int N, int K, const float* lw, const float* lb, int epi,
-                 const void* R, void* Y, int64_t ldy, int Mrows) -> int {
+                 const void* R, void* Y, int64_t ldy, int Mrows, int64_t coff = -1) -> int {
     LinearArgs a{};
     a.X = X; a.ldx = ldx; a.W = blob + woff; a.Y = Y; a.ldy = ldy; a.R = R; a.ldr = ldy;
     a.ln_w = lw; a.ln_b = lb; a.eps = c.layer_norm_eps;
+    if (lw != nullptr && c.dtype == PTTS_BF16) {  // bf16: LayerNorm folded into the weights at load (ptts_decoder_finalize)
+      a.c1 = (const float*)(blob + coff); a.c2 = a.c1 + N;
+    }
     a.M = Mrows; a.N = N; a.K = K; a.Kc = (K > H && K % H == 0) ? H : K;
     a.epi = epi; a.act = c.activation; a.ctrl = ctrl;
     s->launches++;
@@ -316,7 +340,7 @@ static int run_forward(ptts_session* s, cudaStream_t st, bool prefill, const voi
       s->launches++;
     }
     if (int e = lin(x, H, lb + L.wqkv, L.qkv_rows, H, (const float*)(blob + lb + L.ln1_w), (const float*)(blob + lb + L.ln1_b),
-                    EPI_STORE, nullptr, ws + W.qkv, L.qkv_rows, M)) return e;
+                    EPI_STORE, nullptr, ws + W.qkv, L.qkv_rows, M, lb + L.c_qkv)) return e;
     AttnArgs at{};
     at.q = ws + W.qkv; at.ldq = L.qkv_rows; at.q_col0 = 0;
     at.knew = ws + W.qkv; at.vnew = ws + W.qkv; at.ldkv = L.qkv_rows; at.k_col0 = L.nh * D; at.v_col0 = (L.nh + L.nkv) * D;
@@ -335,7 +359,7 @@ static int run_forward(ptts_session* s, cudaStream_t st, bool prefill, const voi
     s->launches++;
     if (int e = lin(ws + W.attn, H, lb + L.wo, H, H, nullptr, nullptr, EPI_RESIDUAL, x, x, H, M)) return e;
     if (int e = lin(x, H, lb + L.wqc, H, H, (const float*)(blob + lb + L.ln2_w), (const float*)(blob + lb + L.ln2_b),
-                    EPI_STORE, nullptr, ws + W.qc, H, M)) return e;
+                    EPI_STORE, nullptr, ws + W.qc, H, M, lb + L.c_qc)) return e;
     AttnArgs ct = at;
     ct.q = ws + W.qc; ct.ldq = H; ct.q_col0 = 0;
     ct.knew = ct.vnew = nullptr;
@@ -348,13 +372,13 @@ static int run_forward(ptts_session* s, cudaStream_t st, bool prefill, const voi
     s->launches++;
     if (int e = lin(ws + W.attn, H, lb + L.woc, H, H, nullptr, nullptr, EPI_RESIDUAL, x, x, H, M)) return e;
     if (int e = lin(x, H, lb + L.fc1, L.F, H, (const float*)(blob + lb + L.ln3_w), (const float*)(blob + lb + L.ln3_b),
-                    EPI_ACT, nullptr, ws + W.hbuf, L.F, M)) return e;
+                    EPI_ACT, nullptr, ws + W.hbuf, L.F, M, lb + L.c_fc1)) return e;
     if (int e = lin(ws + W.hbuf, L.F, lb + L.fc2, H, L.F, nullptr, nullptr, EPI_RESIDUAL, x, x, H, M)) return e;
   }
   // final LayerNorm + K lm heads on the last position of every batch row -> f32 logits [B, K*V] == [B*K, V]
   const char* xlast = ws + W.x + (int64_t)(q_len - 1) * H * es;
   return lin(xlast, (int64_t)q_len * H, L.heads, L.K * L.V, H, (const float*)(blob + L.final_ln_w), (const float*)(blob + L.final_ln_b),
-             EPI_F32, nullptr, ws + W.logits, (int64_t)L.K * L.V, B);
+             EPI_F32, nullptr, ws + W.logits, (int64_t)L.K * L.V, B, L.c_heads);
 }
 
 int ptts_prefill(ptts_session* s, const void* prompt_hidden, const int64_t* prompt_mask, const void* enc_hidden,
@@ -494,6 +518,17 @@ int ptts_op_linear(const ptts_decoder_config* cfg, const void* blob, int32_t ten
     }
     a.ln_w = (const float*)((const char*)blob + w);
     a.ln_b = (const float*)((const char*)blob + b);
+    if (cfg->dtype == PTTS_BF16) {
+      int64_t co = 0;
+      switch (tensor_id) {
+        case PTTS_T_SELF_Q: case PTTS_T_SELF_K: case PTTS_T_SELF_V: co = lb + L.c_qkv; break;
+        case PTTS_T_CROSS_Q: co = lb + L.c_qc; break;
+        case PTTS_T_FC1: co = lb + L.c_fc1; break;
+        default: co = L.c_heads; break;
+      }
+      a.c1 = (const float*)((const char*)blob + co);
+      a.c2 = a.c1 + ms.N;
+    }
   }
   a.eps = cfg->layer_norm_eps;
   a.M = M; a.N = ms.N; a.K = ms.K; a.Kc = (ms.K > L.H && ms.K % L.H == 0) ? L.H : ms.K;

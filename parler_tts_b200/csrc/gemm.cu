@@ -18,6 +18,7 @@
 // The f32 model dtype (config 1, CPU-parity runs) uses a plain SIMT tile kernel.
 #include "common.cuh"
 #include "kernels.h"
+#include "ln_stats.cuh"
 
 namespace ptts {
 
@@ -43,48 +44,10 @@ constexpr int GEMM_THREADS = 256;
 constexpr int GEMM_WARPS = 8;
 constexpr int TILE_M = 32;
 
-// In-place LayerNorm of the staged tile (rows x Kc, row stride lds), fp32 two-pass statistics.
-// Same lane->element mapping and summation order as step.cu::ln_tile (the two paths are compared bitwise).
-__device__ __forceinline__ void unpack8g(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; i++) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
-}
-__device__ void tile_layernorm(bf16* xs, int lds, int Kc, const float* __restrict__ g, const float* __restrict__ b, float eps) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < TILE_M; r += GEMM_WARPS) {
-    bf16* row = xs + r * lds;
-    float s = 0.f;
-    for (int c = lane * 8; c < Kc; c += 256) {
-      float f[8];
-      unpack8g(*reinterpret_cast<const uint4*>(row + c), f);
-      s += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
-    }
-    const float mean = warp_sum(s) / (float)Kc;
-    float q = 0.f;
-    for (int c = lane * 8; c < Kc; c += 256) {
-      float f[8];
-      unpack8g(*reinterpret_cast<const uint4*>(row + c), f);
-#pragma unroll
-      for (int e = 0; e < 8; e++) { const float d = f[e] - mean; q = fmaf(d, d, q); }
-    }
-    const float rstd = rsqrtf(warp_sum(q) / (float)Kc + eps);
-    for (int c = lane * 8; c < Kc; c += 256) {
-      float f[8];
-      unpack8g(*reinterpret_cast<const uint4*>(row + c), f);
-      uint4 o;
-      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-      for (int e = 0; e < 4; e++)
-        oh[e] = __floats2bfloat162_rn((f[2 * e] - mean) * rstd * g[c + 2 * e] + b[c + 2 * e], (f[2 * e + 1] - mean) * rstd * g[c + 2 * e + 1] + b[c + 2 * e + 1]);
-      *reinterpret_cast<uint4*>(row + c) = o;
-    }
-  }
-}
-
 template <int NT, int PF>
 __global__ void __launch_bounds__(GEMM_THREADS) linear_bf16_kernel(LinearArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float ln_stats[64];  // (mean, rstd) per row when LayerNorm is folded in
   bf16* xs = reinterpret_cast<bf16*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Kc = p.Kc, lds = Kc + 8;
@@ -139,10 +102,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) linear_bf16_kernel(LinearArgs p)
       *reinterpret_cast<uint4*>(xs + r * lds + cv * 8) = val;
     }
     __syncthreads();
-    if (p.ln_w != nullptr) {
-      tile_layernorm(xs, lds, Kc, p.ln_w, p.ln_b, p.eps);
-      __syncthreads();
-    }
+    if (p.c1 != nullptr) tile_row_stats(xs, lds, Kc, p.M - m0, p.eps, ln_stats);  // published by the barrier before the epilogue
     const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;
     const int lcol = (lane >> 4) * 8;
     for (int i0 = 0; i0 < per_chunk; i0 += PF) {
@@ -195,6 +155,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) linear_bf16_kernel(LinearArgs p)
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < GEMM_WARPS; w++) v += red[((size_t)w * TILE_M + r) * FB + cidx];
+    if (p.c1 != nullptr) v = ln_stats[2 * r + 1] * (v - ln_stats[2 * r] * p.c1[n0 + cidx]) + p.c2[n0 + cidx];
     v = DT<bf16>::rnd(v);  // nn.Linear output is rounded to the model dtype
     const size_t yo = (size_t)(m0 + r) * p.ldy + n0 + cidx;
     if (p.epi == EPI_ACT) {
@@ -377,6 +338,39 @@ int pack_matrix(const void* src, int src_dtype, int64_t rows, int64_t cols, int 
     if (src_dtype == PTTS_BF16) pack_plain_kernel<bf16, float><<<blocks, threads, 0, st>>>((const bf16*)src, n, d);
     else pack_plain_kernel<float, float><<<blocks, threads, 0, st>>>((const float*)src, n, d);
   }
+  PTTS_LAUNCH_CHECK();
+  return PTTS_OK;
+}
+
+// W (fragment order, bf16) <- bf16(gamma_k * W_nk);  c1_n = sum_k W'_nk;  c2_n = sum_k beta_k * W_nk   (one block per row n)
+__global__ void __launch_bounds__(128) fold_layernorm_kernel(bf16* __restrict__ wp, int K, const float* __restrict__ g, const float* __restrict__ b,
+                                                             float* __restrict__ c1, float* __restrict__ c2) {
+  __shared__ float sh[8];
+  const int n = blockIdx.x;
+  const int64_t nt = n >> 3, gq = n & 7;
+  float a1 = 0.f, a2 = 0.f;
+  for (int k = threadIdx.x; k < K; k += 128) {
+    const int64_t kt = k >> 5;
+    const int kk = k & 31, j = kk >> 4, c = kk & 15, half = c >> 3, t = (c & 7) >> 1, e = c & 1;
+    const int64_t off = ((nt * (K >> 5) + kt) * 32 + (gq * 4 + t)) * 8 + (j * 2 + half) * 2 + e;
+    const float w = __bfloat162float(wp[off]);
+    a2 = fmaf(b[k], w, a2);
+    const bf16 wf = __float2bfloat16_rn(g[k] * w);
+    wp[off] = wf;
+    a1 += __bfloat162float(wf);
+  }
+  a1 = warp_sum(a1);
+  a2 = warp_sum(a2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[warp] = a1; sh[4 + warp] = a2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    c1[n] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
+    c2[n] = (sh[4] + sh[5]) + (sh[6] + sh[7]);
+  }
+}
+int fold_layernorm(void* w_packed, int N, int K, const float* gamma, const float* beta, float* c1, float* c2, cudaStream_t st) {
+  fold_layernorm_kernel<<<N, 128, 0, st>>>((bf16*)w_packed, K, gamma, beta, c1, c2);
   PTTS_LAUNCH_CHECK();
   return PTTS_OK;
 }

@@ -11,13 +11,15 @@ struct LinearArgs {
   const void* W;               // packed weight slot (fragment order for bf16, row-major for f32)
   void* Y; int64_t ldy;
   const void* R; int64_t ldr;  // residual (EPI_RESIDUAL)
-  const float* ln_w; const float* ln_b; float eps;  // fused LayerNorm on x (needs Kc == K)
+  const float* ln_w; const float* ln_b; float eps;  // fused LayerNorm on x (needs Kc == K); f32 path uses gamma/beta directly
+  const float* c1; const float* c2;                 // bf16 path: folded LayerNorm vectors (ln_stats.cuh); LN on iff c1 != nullptr
   int M, N, K, Kc;             // Kc = activation tile width (0 = choose)
   int epi, act;
   const Ctrl* ctrl;            // device control block: kernels no-op once generation has finished
 };
 int launch_linear(const LinearArgs& a, int dtype, cudaStream_t st, bool pdl, int sm_count);
 int pack_matrix(const void* src, int src_dtype, int64_t rows, int64_t cols, int row_off, int K, void* dst, int dst_dtype, cudaStream_t st);
+int fold_layernorm(void* w_packed, int N, int K, const float* gamma, const float* beta, float* c1, float* c2, cudaStream_t st);
 int pack_plain(const void* src, int src_dtype, int64_t n, void* dst, int dst_dtype, cudaStream_t st);
 
 // ---- attention (attention.cu) -------------------------------------------------------------------

@@ -23,7 +23,8 @@ struct DecoderLayout {
   int64_t embed, pos, layer0, layer_stride;
   // offsets inside one layer
   int64_t ln1_w, ln1_b, wqkv, wo, ln2_w, ln2_b, wqc, wkvc, woc, ln3_w, ln3_b, fc1, fc2;
-  int64_t final_ln_w, final_ln_b, heads, rope_cos, rope_sin;
+  int64_t c_qkv, c_qc, c_fc1;   // folded-LayerNorm vectors (c1 | c2), f32, per layer (ln_stats.cuh)
+  int64_t final_ln_w, final_ln_b, heads, rope_cos, rope_sin, c_heads;
   int64_t total;
 };
 
@@ -52,12 +53,16 @@ static inline DecoderLayout make_layout(const ptts_decoder_config& c) {
   l.ln3_w = take(l.H * 4) - base; l.ln3_b = take(l.H * 4) - base;
   l.fc1 = take((int64_t)l.F * l.H * l.es) - base;
   l.fc2 = take((int64_t)l.H * l.F * l.es) - base;
+  l.c_qkv = take((int64_t)2 * l.qkv_rows * 4) - base;
+  l.c_qc = take((int64_t)2 * l.H * 4) - base;
+  l.c_fc1 = take((int64_t)2 * l.F * 4) - base;
   l.layer_stride = o - base;
   o = base + l.layer_stride * l.L;
   l.final_ln_w = take(l.H * 4); l.final_ln_b = take(l.H * 4);
   l.heads = take((int64_t)l.K * l.V * l.H * l.es);
   l.rope_cos = take(c.rope ? (int64_t)c.max_positions * PTTS_HEAD_DIM * l.es : 0);
   l.rope_sin = take(c.rope ? (int64_t)c.max_positions * PTTS_HEAD_DIM * l.es : 0);
+  l.c_heads = take((int64_t)2 * l.K * l.V * 4);
   l.total = o;
   return l;
 }

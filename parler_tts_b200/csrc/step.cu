@@ -20,6 +20,7 @@
 #include "attn_core.cuh"
 #include "common.cuh"
 #include "kernels.h"
+#include "ln_stats.cuh"
 #include "sample_core.cuh"
 #include "step.h"
 
@@ -114,7 +115,7 @@ __device__ __forceinline__ void prof_mark(long long* prof, int slot) {
 // ---- shared-memory context ----------------------------------------------------------------------
 struct Smem {
   uint64_t* bars;   // [2] tile buffers
-  float* lnp;       // [2*H] gamma | beta
+  float* stats;     // [64] (mean, rstd) per row of the staged tile
   bf16* tile[2];    // activation tile buffers, row pitch = H + 8
   unsigned char* scratch;  // start of the tile region (aliased by the K-reduction buffer and by attention)
   uint32_t parity;  // bit i: parity to wait for on bars[i]
@@ -141,69 +142,11 @@ __device__ __forceinline__ void wait_tile(Smem& sm, int buf) {
   sm.parity ^= (1u << buf);
 }
 
-// In-place LayerNorm of the staged tile.  Each warp owns rows warp, warp+8, warp+16, warp+24 and walks them
-// TOGETHER (4 independent chains), 8 elements (one LDS.128) per lane per step; 3 passes over shared memory
-// (mean, variance, normalise -- the two-pass statistics torch uses), no per-thread arrays.
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; i++) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
-}
-__device__ __forceinline__ void ln_tile(bf16* xs, int pitch, int Kc, int M, const float* __restrict__ lnp, int H, float eps) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  bf16* row[4];
-  bool ok[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) { ok[i] = warp + 8 * i < M; row[i] = xs + (size_t)(warp + 8 * (ok[i] ? i : 0)) * pitch; }
-  float s[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int c = lane * 8; c < Kc; c += 256) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(row[i] + c), f);
-      s[i] += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
-    }
-  }
-  float mean[4], q[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < 4; i++) mean[i] = warp_sum(s[i]) / (float)Kc;
-  for (int c = lane * 8; c < Kc; c += 256) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(row[i] + c), f);
-#pragma unroll
-      for (int e = 0; e < 8; e++) { const float d = f[e] - mean[i]; q[i] = fmaf(d, d, q[i]); }
-    }
-  }
-  float rstd[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) rstd[i] = rsqrtf(warp_sum(q[i]) / (float)Kc + eps);
-  for (int c = lane * 8; c < Kc; c += 256) {
-    float g[8], bb[8];
-    *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(lnp + c);
-    *reinterpret_cast<float4*>(g + 4) = *reinterpret_cast<const float4*>(lnp + c + 4);
-    *reinterpret_cast<float4*>(bb) = *reinterpret_cast<const float4*>(lnp + H + c);
-    *reinterpret_cast<float4*>(bb + 4) = *reinterpret_cast<const float4*>(lnp + H + c + 4);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(row[i] + c), f);
-      uint4 o;
-      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-      for (int e = 0; e < 4; e++)
-        oh[e] = __floats2bfloat162_rn((f[2 * e] - mean[i]) * rstd[i] * g[2 * e] + bb[2 * e], (f[2 * e + 1] - mean[i]) * rstd[i] * g[2 * e + 1] + bb[2 * e + 1]);
-      if (ok[i]) *reinterpret_cast<uint4*>(row[i] + c) = o;
-    }
-  }
-}
-
 struct GemmDesc {
   const bf16* X; int64_t ldx;
   const uint4* W;
   int N, K;
-  const float* lnw; const float* lnb;
+  const float* c1; const float* c2;  // folded LayerNorm vectors (ln_stats.cuh) or nullptr
   int epi;
   const bf16* R;
   void* Y; int64_t ldy;
@@ -228,21 +171,13 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
 #pragma unroll
       for (int j = 0; j < NT; j++) dst[j] = ldg_stream_s(d.W + ((size_t)(nt0 + j) * KT + ktg) * 32 + lane);
     };
+    // activations first (they are the critical path: the weights are already L2-resident), chunk 0 and, when
+    // double-buffered, chunk 1; then the first PF weight slabs of this warp
+    stage_tile(sm, 0, d.X, d.ldx, 0, Kc, M);
+    if (sm.nbuf > 1 && n_chunks > 1) stage_tile(sm, 1, d.X, d.ldx, Kc, Kc, M);
 #pragma unroll
     for (int s = 0; s < PF; s++)
       if (s < per_chunk) load_w(wr[s], 0, s);
-    // activations: chunk 0 (and chunk 1 when double-buffered)
-    stage_tile(sm, 0, d.X, d.ldx, 0, Kc, M);
-    if (sm.nbuf > 1 && n_chunks > 1) stage_tile(sm, 1, d.X, d.ldx, Kc, Kc, M);
-    if (d.lnw != nullptr) {
-      // gamma | beta -> shared (vector loads, all in flight)
-      for (int i = threadIdx.x * 4; i < H; i += ST_THREADS * 4) {
-        const float4 g4 = *reinterpret_cast<const float4*>(d.lnw + i);
-        const float4 b4 = *reinterpret_cast<const float4*>(d.lnb + i);
-        *reinterpret_cast<float4*>(sm.lnp + i) = g4;
-        *reinterpret_cast<float4*>(sm.lnp + H + i) = b4;
-      }
-    }
     float acc[2][NT][4];
 #pragma unroll
     for (int a = 0; a < 2; a++)
@@ -263,11 +198,7 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
       }
       wait_tile(sm, buf);
       if (c == 0) prof_mark(sm.prof, 1);
-      if (d.lnw != nullptr) {
-        __syncthreads();  // lnp visible
-        ln_tile(sm.tile[buf], sm.pitch, Kc, M, sm.lnp, H, p.eps);
-        __syncthreads();
-      }
+      if (d.c1 != nullptr) tile_row_stats(sm.tile[buf], sm.pitch, Kc, M, p.eps, sm.stats);  // (mean, rstd) per row; read in the epilogue
       if (c == 0) prof_mark(sm.prof, 2);
       const bf16* xs = sm.tile[buf];
       for (int i0 = 0; i0 < per_chunk; i0 += PF) {
@@ -320,6 +251,7 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
       float v = 0.f;
 #pragma unroll
       for (int w = 0; w < ST_WARPS; w++) v += red[((size_t)w * 32 + r) * FB + cidx];
+      if (d.c1 != nullptr) v = sm.stats[2 * r + 1] * (v - sm.stats[2 * r] * d.c1[n0 + cidx]) + d.c2[n0 + cidx];
       v = DT<bf16>::rnd(v);
       const size_t yo = (size_t)r * d.ldy + n0 + cidx;
       if (d.epi == EPI_ACT) v = apply_act(v, p.act);
@@ -364,10 +296,12 @@ __device__ __forceinline__ void attn_phase(const StepParams& p, Smem& sm, const 
 // L2 prefetch of the K/V rows this CTA's warps will read in the coming attention phases of layer l.
 __device__ __forceinline__ void prefetch_kv(const StepParams& p, int l, int pos) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < 4) return;  // warps 0-3 go straight to the GEMM (warp 0 issues its TMA tile copies)
+  const int pw = warp - 4;  // 4 prefetching warps cover the CTA's items
   if (pos > 0 && lane == 0) {
     const char* kc = p.self_kv + p.self_layer_stride * l;
     const size_t vofs = (size_t)p.B * p.nkv * p.Tmax * HD * 2;
-    for (int it = blockIdx.x + gridDim.x * warp; it < p.B * p.nkv; it += gridDim.x * ST_WARPS) {  // (any warp may prefetch any item)
+    for (int it = blockIdx.x + gridDim.x * pw; it < p.B * p.nkv; it += gridDim.x * 4) {  // (any warp may prefetch any item)
       const char* k = kc + (size_t)it * p.Tmax * HD * 2;  // [B][nkv][Tmax][64]: item-major
       l2_prefetch(k, (uint32_t)(pos * HD * 2));
       l2_prefetch(k + vofs, (uint32_t)(pos * HD * 2));
@@ -376,7 +310,7 @@ __device__ __forceinline__ void prefetch_kv(const StepParams& p, int l, int pos)
   if (lane == 0) {  // cross K/V of this CTA's items (item-major, contiguous)
     const char* ck = p.cross_kv + p.cross_layer_stride * l;
     const size_t vofs = (size_t)p.B * p.nckv * p.S * HD * 2;
-    for (int it = blockIdx.x + gridDim.x * warp; it < p.B * p.nckv; it += gridDim.x * ST_WARPS) {
+    for (int it = blockIdx.x + gridDim.x * pw; it < p.B * p.nckv; it += gridDim.x * 4) {
       const char* k = ck + (size_t)it * p.S * HD * 2;
       l2_prefetch(k, (uint32_t)(p.S * HD * 2));
       l2_prefetch(k + vofs, (uint32_t)(p.S * HD * 2));
@@ -403,8 +337,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
 
   Smem sm;
   sm.bars = reinterpret_cast<uint64_t*>(smem_raw);
-  sm.lnp = reinterpret_cast<float*>(smem_raw + 256);
-  sm.scratch = smem_raw + 256 + (size_t)2 * H * sizeof(float);
+  sm.stats = reinterpret_cast<float*>(smem_raw + 256);
+  sm.scratch = smem_raw + 512;
   sm.pitch = H + 8;
   sm.nbuf = p.nbuf;
   sm.tile[0] = reinterpret_cast<bf16*>(sm.scratch);
@@ -432,9 +366,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
   if (tid == 0) {
     const char* lb = blob + p.layer0;
     prefetch_slice(lb + p.wqkv, p.qkv_rows, H, p.nt_qkv);
-    l2_prefetch(lb + p.ln1_w, (uint32_t)H * 4); l2_prefetch(lb + p.ln1_b, (uint32_t)H * 4);
-    l2_prefetch(lb + p.ln2_w, (uint32_t)H * 4); l2_prefetch(lb + p.ln2_b, (uint32_t)H * 4);
-    l2_prefetch(lb + p.ln3_w, (uint32_t)H * 4); l2_prefetch(lb + p.ln3_b, (uint32_t)H * 4);
+    l2_prefetch(lb + p.c_qkv, (uint32_t)p.qkv_rows * 8); l2_prefetch(lb + p.c_qc, (uint32_t)H * 8); l2_prefetch(lb + p.c_fc1, (uint32_t)p.F * 8);
     prefetch_slice(lb + p.wo, H, H, p.nt_h);
     prefetch_slice(lb + p.wqc, H, H, p.nt_h);
     prefetch_slice(lb + p.woc, H, H, p.nt_h);
@@ -469,7 +401,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
     prof_mark(sm.prof, 0);
     const char* lb = blob + p.layer0 + p.layer_stride * (l < p.L ? l : p.L - 1);
     if (sub == 0) prefetch_kv(p, l, pos);
-    if (tid == 0) {
+    if (tid == ST_THREADS - 32) {
       // Pull the NEXT layer's weights into L2 while this layer runs, one matrix per phase (the matrix phase `sub`
       // of the next layer will use), so the HBM stream is spread over the layer instead of colliding with one
       // phase's activation staging.  LayerNorm parameters ride along (they would otherwise be cold HBM reads
@@ -478,13 +410,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
       const char* nb = lb + p.layer_stride;
       switch (sub) {
         case 0:
-          if (!last) { prefetch_slice(nb + p.wqkv, p.qkv_rows, H, p.nt_qkv); l2_prefetch(nb + p.ln1_w, (uint32_t)H * 4); l2_prefetch(nb + p.ln1_b, (uint32_t)H * 4); }
-          else { prefetch_slice(blob + p.heads, p.K * p.V, H, p.nt_heads); l2_prefetch(blob + p.final_ln_w, (uint32_t)H * 4); l2_prefetch(blob + p.final_ln_b, (uint32_t)H * 4); }
+          if (!last) { prefetch_slice(nb + p.wqkv, p.qkv_rows, H, p.nt_qkv); l2_prefetch(nb + p.c_qkv, (uint32_t)p.qkv_rows * 8); }
+          else { prefetch_slice(blob + p.heads, p.K * p.V, H, p.nt_heads); l2_prefetch(blob + p.c_heads, (uint32_t)(p.K * p.V) * 8); }
           break;
         case 2: if (!last) prefetch_slice(nb + p.wo, H, H, p.nt_h); break;
-        case 3: if (!last) { prefetch_slice(nb + p.wqc, H, H, p.nt_h); l2_prefetch(nb + p.ln2_w, (uint32_t)H * 4); l2_prefetch(nb + p.ln2_b, (uint32_t)H * 4); } break;
+        case 3: if (!last) { prefetch_slice(nb + p.wqc, H, H, p.nt_h); l2_prefetch(nb + p.c_qc, (uint32_t)H * 8); } break;
         case 5: if (!last) prefetch_slice(nb + p.woc, H, H, p.nt_h); break;
-        case 6: if (!last) { prefetch_slice(nb + p.fc1, p.F, H, p.nt_fc1); l2_prefetch(nb + p.ln3_w, (uint32_t)H * 4); l2_prefetch(nb + p.ln3_b, (uint32_t)H * 4); } break;
+        case 6: if (!last) { prefetch_slice(nb + p.fc1, p.F, H, p.nt_fc1); l2_prefetch(nb + p.c_fc1, (uint32_t)p.F * 8); } break;
         case 7: if (!last) prefetch_slice(nb + p.fc2, H, p.F, p.nt_h); break;
         default: break;
       }
@@ -516,31 +448,31 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
       int nt = p.nt_h;
       switch (sub) {
         case 0:  // qkv = LN1(x) Wqkv^T
-          g = GemmDesc{p.x, H, reinterpret_cast<const uint4*>(lb + p.wqkv), p.qkv_rows, H, reinterpret_cast<const float*>(lb + p.ln1_w),
-                       reinterpret_cast<const float*>(lb + p.ln1_b), EPI_STORE, nullptr, p.qkv, p.qkv_rows};
+          g = GemmDesc{p.x, H, reinterpret_cast<const uint4*>(lb + p.wqkv), p.qkv_rows, H, reinterpret_cast<const float*>(lb + p.c_qkv),
+                       reinterpret_cast<const float*>(lb + p.c_qkv) + p.qkv_rows, EPI_STORE, nullptr, p.qkv, p.qkv_rows};
           nt = p.nt_qkv;
           break;
         case 2:  // x += attn Wo^T
           g = GemmDesc{p.attn, H, reinterpret_cast<const uint4*>(lb + p.wo), H, H, nullptr, nullptr, EPI_RESIDUAL, p.x, p.x, H};
           break;
         case 3:  // q_cross = LN2(x) Wq^T
-          g = GemmDesc{p.x, H, reinterpret_cast<const uint4*>(lb + p.wqc), H, H, reinterpret_cast<const float*>(lb + p.ln2_w),
-                       reinterpret_cast<const float*>(lb + p.ln2_b), EPI_STORE, nullptr, p.qc, H};
+          g = GemmDesc{p.x, H, reinterpret_cast<const uint4*>(lb + p.wqc), H, H, reinterpret_cast<const float*>(lb + p.c_qc),
+                       reinterpret_cast<const float*>(lb + p.c_qc) + H, EPI_STORE, nullptr, p.qc, H};
           break;
         case 5:  // x += attn Wo_cross^T
           g = GemmDesc{p.attn, H, reinterpret_cast<const uint4*>(lb + p.woc), H, H, nullptr, nullptr, EPI_RESIDUAL, p.x, p.x, H};
           break;
         case 6:  // h = act(LN3(x) W1^T)
-          g = GemmDesc{p.x, H, reinterpret_cast<const uint4*>(lb + p.fc1), p.F, H, reinterpret_cast<const float*>(lb + p.ln3_w),
-                       reinterpret_cast<const float*>(lb + p.ln3_b), EPI_ACT, nullptr, p.hbuf, p.F};
+          g = GemmDesc{p.x, H, reinterpret_cast<const uint4*>(lb + p.fc1), p.F, H, reinterpret_cast<const float*>(lb + p.c_fc1),
+                       reinterpret_cast<const float*>(lb + p.c_fc1) + p.F, EPI_ACT, nullptr, p.hbuf, p.F};
           nt = p.nt_fc1;
           break;
         case 7:  // x += h W2^T
           g = GemmDesc{p.hbuf, p.F, reinterpret_cast<const uint4*>(lb + p.fc2), H, p.F, nullptr, nullptr, EPI_RESIDUAL, p.x, p.x, H};
           break;
         default:  // final LayerNorm + K lm heads -> f32 logits [B, K*V]
-          g = GemmDesc{p.x, H, reinterpret_cast<const uint4*>(blob + p.heads), p.K * p.V, H, reinterpret_cast<const float*>(blob + p.final_ln_w),
-                       reinterpret_cast<const float*>(blob + p.final_ln_b), EPI_F32, nullptr, p.logits, (int64_t)p.K * p.V};
+          g = GemmDesc{p.x, H, reinterpret_cast<const uint4*>(blob + p.heads), p.K * p.V, H, reinterpret_cast<const float*>(blob + p.c_heads),
+                       reinterpret_cast<const float*>(blob + p.c_heads) + p.K * p.V, EPI_F32, nullptr, p.logits, (int64_t)p.K * p.V};
           nt = p.nt_heads;
           break;
       }
@@ -571,7 +503,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
 
 // ---- host side ----------------------------------------------------------------------------------
 int step_smem_bytes(const StepParams& p) {
-  return (int)(256 + (size_t)2 * p.H * sizeof(float) + p.tile_region_bytes);
+  return (int)(512 + p.tile_region_bytes);
 }
 
 int launch_decode_step(const StepParams& p, int grid, cudaStream_t st) {

@@ -12,6 +12,7 @@ struct StepParams {
   // packed weights
   const char* blob;
   int64_t embed, pos, layer0, layer_stride, ln1_w, ln1_b, wqkv, wo, ln2_w, ln2_b, wqc, woc, ln3_w, ln3_b, fc1, fc2;
+  int64_t c_qkv, c_qc, c_fc1, c_heads;   // folded-LayerNorm vectors
   int64_t final_ln_w, final_ln_b, heads, rope_cos, rope_sin;
   // workspace
   bf16 *x, *qkv, *attn, *qc, *hbuf;

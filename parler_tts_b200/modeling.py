@@ -172,6 +172,7 @@ class DecoderEngine:
                 self._pack(tid, i, need(f"{p}layers.{i}.{nm}"))
         self._pack(L.T_FINAL_LN_W, 0, need(p + "layer_norm.weight"))
         self._pack(L.T_FINAL_LN_B, 0, need(p + "layer_norm.bias"))
+        _lib.check(_lib.lib().ptts_decoder_finalize(C.byref(self.c), _lib.ptr(self.blob), _lib.stream_ptr()))
         torch.cuda.current_stream().synchronize()
         return self
 

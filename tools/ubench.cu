@@ -140,6 +140,61 @@ __global__ void __launch_bounds__(256, 1) k_ln(Res* res, int reps) {
   if (tid == 0) res[blockIdx.x].t[0] = (t1 - t0) / reps;
 }
 
+// vectorised LayerNorm (LDS.128, the version in step.cu)
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__global__ void __launch_bounds__(256, 1) k_ln_vec(Res* res, int reps) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  bf16* xs = reinterpret_cast<bf16*>(smem + 128);
+  float* lnp = reinterpret_cast<float*>(smem + 128 + 32 * 1032 * 2);
+  const int pitch = 1032, Kc = 1024, H = 1024;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 32 * pitch; i += 256) xs[i] = __float2bfloat16((float)((i * 37) % 101) * 0.01f);
+  for (int i = tid; i < 2 * H; i += 256) lnp[i] = 1.0f + (i % 7) * 0.01f;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < reps; it++) {
+    bf16* row[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) row[i] = xs + (size_t)(warp + 8 * i) * pitch;
+    float s[4] = {0, 0, 0, 0};
+    for (int c = lane * 8; c < Kc; c += 256)
+#pragma unroll
+      for (int i = 0; i < 4; i++) { float f[8]; unpack8(*reinterpret_cast<const uint4*>(row[i] + c), f); s[i] += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7])); }
+    float mean[4], q[4] = {0, 0, 0, 0}, rstd[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { float v = s[i]; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); mean[i] = v / Kc; }
+    for (int c = lane * 8; c < Kc; c += 256)
+#pragma unroll
+      for (int i = 0; i < 4; i++) { float f[8]; unpack8(*reinterpret_cast<const uint4*>(row[i] + c), f);
+#pragma unroll
+        for (int e = 0; e < 8; e++) { const float d = f[e] - mean[i]; q[i] = fmaf(d, d, q[i]); } }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { float v = q[i]; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); rstd[i] = rsqrtf(v / Kc + 1e-5f); }
+    for (int c = lane * 8; c < Kc; c += 256) {
+      float g[8], bb[8];
+      *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(lnp + c);
+      *reinterpret_cast<float4*>(g + 4) = *reinterpret_cast<const float4*>(lnp + c + 4);
+      *reinterpret_cast<float4*>(bb) = *reinterpret_cast<const float4*>(lnp + H + c);
+      *reinterpret_cast<float4*>(bb + 4) = *reinterpret_cast<const float4*>(lnp + H + c + 4);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float f[8]; unpack8(*reinterpret_cast<const uint4*>(row[i] + c), f);
+        uint4 o; __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; e++) oh[e] = __floats2bfloat162_rn((f[2 * e] - mean[i]) * rstd[i] * g[2 * e] + bb[2 * e], (f[2 * e + 1] - mean[i]) * rstd[i] * g[2 * e + 1] + bb[2 * e + 1]);
+        *reinterpret_cast<uint4*>(row[i] + c) = o;
+      }
+    }
+    __syncthreads();
+  }
+  long long t1 = clock64();
+  if (tid == 0) res[blockIdx.x].t[0] = (t1 - t0) / reps;
+}
+
 // pure barrier cost
 __global__ void __launch_bounds__(256, 1) k_bar(unsigned* ctr, Res* res, int reps, int mode) {
   unsigned target = 0;
@@ -201,6 +256,13 @@ int main() {
     CK(cudaLaunchCooperativeKernel((void*)k_ln, dim3(grid), dim3(256), args, smem, 0));
     CK(cudaDeviceSynchronize());
     report("layernorm 32x1024 tile (smem only)", res, grid, 1);
+  }
+  {
+    CK(cudaFuncSetAttribute(k_ln_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    void* args[] = {&res, &reps};
+    CK(cudaLaunchCooperativeKernel((void*)k_ln_vec, dim3(grid), dim3(256), args, smem, 0));
+    CK(cudaDeviceSynchronize());
+    report("layernorm vectorised (LDS.128)", res, grid, 1);
   }
   printf("done\n");
   return 0;
