@@ -271,6 +271,7 @@ static bool setup_fused(ptts_session* s) {
   if (p.sample_items > 72) return false;
   p.do_sample_phase = 1;
   p.prof = s->prof;
+  { const char* d = getenv("PTTS_DBG"); p.dbg = d ? atoi(d) : 0; }
   return true;
 }
 

@@ -32,13 +32,18 @@ __device__ __forceinline__ void tile_row_stats(const bf16* xs, int pitch, int Kc
     shift[i] = __bfloat162float(row[i][0]);
   }
   for (int c = lane * 8; c < Kc; c += 256) {
+    uint4 u[4];  // register copies (4 LDS.128 in flight); binding a reference to shared memory would re-read 32-bit words
+#pragma unroll
+    for (int i = 0; i < 4; i++) u[i] = *reinterpret_cast<const uint4*>(row[i] + c);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       float f[8];
-      unpack8_bf16(*reinterpret_cast<const uint4*>(row[i] + c), f);
-      float a = 0.f, q = 0.f;
+      unpack8_bf16(u[i], f);
 #pragma unroll
-      for (int e = 0; e < 8; e++) { const float d = f[e] - shift[i]; a += d; q = fmaf(d, d, q); }
+      for (int e = 0; e < 8; e++) f[e] -= shift[i];
+      // fixed pairwise order (short dependency chains)
+      const float a = ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+      const float q = (fmaf(f[1], f[1], f[0] * f[0]) + fmaf(f[3], f[3], f[2] * f[2])) + (fmaf(f[5], f[5], f[4] * f[4]) + fmaf(f[7], f[7], f[6] * f[6]));
       s1[i] += a;
       s2[i] += q;
     }

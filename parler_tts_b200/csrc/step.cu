@@ -116,13 +116,15 @@ __device__ __forceinline__ void prof_mark(long long* prof, int slot) {
 struct Smem {
   uint64_t* bars;   // [2] tile buffers
   float* stats;     // [64] (mean, rstd) per row of the staged tile
-  bf16* tile[2];    // activation tile buffers, row pitch = H + 8
+  bf16* tile0;      // activation tile buffers (tile_of(sm, buf)), row pitch = H + 8
   unsigned char* scratch;  // start of the tile region (aliased by the K-reduction buffer and by attention)
   uint32_t parity;  // bit i: parity to wait for on bars[i]
   long long* prof;  // CTA 0 / thread 0 timestamps of the current phase (nullptr = off)
   int pitch;
   int nbuf;
 };
+
+__device__ __forceinline__ bf16* tile_of(const Smem& sm, int buf) { return sm.tile0 + (size_t)buf * 32 * sm.pitch; }
 
 // TMA-stage x[0:M, col0:col0+Kc] into tile buffer `buf` (called by all threads).
 __device__ __forceinline__ void stage_tile(Smem& sm, int buf, const bf16* X, int64_t ldx, int col0, int Kc, int M) {
@@ -134,7 +136,7 @@ __device__ __forceinline__ void stage_tile(Smem& sm, int buf, const bf16* X, int
     // one bulk copy per row (tools/ubench.cu: 1.23 us for the 64 KB tile with all 148 CTAs reading the same
     // lines -- no L2 hot-spotting; splitting rows into more, staggered copies was 3x slower: per-copy cost)
     if ((int)threadIdx.x < M)
-      bulk_g2s(sm.tile[buf] + (size_t)threadIdx.x * sm.pitch, X + (size_t)threadIdx.x * ldx + col0, (uint32_t)(Kc * 2), &sm.bars[buf]);
+      bulk_g2s(tile_of(sm, buf) + (size_t)threadIdx.x * sm.pitch, X + (size_t)threadIdx.x * ldx + col0, (uint32_t)(Kc * 2), &sm.bars[buf]);
   }
 }
 __device__ __forceinline__ void wait_tile(Smem& sm, int buf) {
@@ -163,7 +165,11 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
   const int per_chunk = (kt_per_chunk > warp) ? (kt_per_chunk - warp + ST_WARPS - 1) / ST_WARPS : 0;
   const int ntasks = d.N / (8 * NT);
   constexpr int FB = 8 * NT;
+  // single-chunk GEMMs with two tile buffers keep the staged tile (and its row statistics) resident across this CTA's
+  // tasks: the K-reduction scratch then lives in the second buffer (lm heads: 2-3 tasks per CTA)
+  const bool resident = (n_chunks == 1 && sm.nbuf > 1);
   for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+    const bool fresh = !resident || task == (int)blockIdx.x;
     const int nt0 = task * NT;
     uint4 wr[PF][NT];
     auto load_w = [&](uint4 (&dst)[NT], int c, int i) {
@@ -173,7 +179,7 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
     };
     // activations first (they are the critical path: the weights are already L2-resident), chunk 0 and, when
     // double-buffered, chunk 1; then the first PF weight slabs of this warp
-    stage_tile(sm, 0, d.X, d.ldx, 0, Kc, M);
+    if (fresh) stage_tile(sm, 0, d.X, d.ldx, 0, Kc, M);
     if (sm.nbuf > 1 && n_chunks > 1) stage_tile(sm, 1, d.X, d.ldx, Kc, Kc, M);
 #pragma unroll
     for (int s = 0; s < PF; s++)
@@ -196,11 +202,11 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
           if (s < per_chunk) load_w(wr[s], c, s);
         if (sm.nbuf == 1) stage_tile(sm, 0, d.X, d.ldx, c * Kc, Kc, M);
       }
-      wait_tile(sm, buf);
+      if (fresh) wait_tile(sm, buf);
       if (c == 0) prof_mark(sm.prof, 1);
-      if (d.c1 != nullptr) tile_row_stats(sm.tile[buf], sm.pitch, Kc, M, p.eps, sm.stats);  // (mean, rstd) per row; read in the epilogue
+      if (fresh && d.c1 != nullptr) tile_row_stats(tile_of(sm, buf), sm.pitch, Kc, M, p.eps, sm.stats);  // (mean, rstd) per row; read in the epilogue
       if (c == 0) prof_mark(sm.prof, 2);
-      const bf16* xs = sm.tile[buf];
+      const bf16* xs = tile_of(sm, buf);
       for (int i0 = 0; i0 < per_chunk; i0 += PF) {
 #pragma unroll
         for (int s = 0; s < PF; s++) {
@@ -229,7 +235,7 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
     }
     prof_mark(sm.prof, 3);
     __syncthreads();
-    float* red = reinterpret_cast<float*>(sm.scratch);  // [8][32][FB], aliases the (now idle) tile buffers
+    float* red = reinterpret_cast<float*>(resident ? tile_of(sm, 1) : tile_of(sm, 0));  // [8][32][FB], in an idle tile buffer
     {
       const int g = lane >> 2, t = lane & 3;
 #pragma unroll
@@ -341,8 +347,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
   sm.scratch = smem_raw + 512;
   sm.pitch = H + 8;
   sm.nbuf = p.nbuf;
-  sm.tile[0] = reinterpret_cast<bf16*>(sm.scratch);
-  sm.tile[1] = sm.tile[0] + (size_t)32 * sm.pitch;
+  sm.tile0 = reinterpret_cast<bf16*>(sm.scratch);
   sm.parity = 0;
   sm.prof = nullptr;
   if (tid == 0) {
@@ -362,7 +367,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
   const char* blob = p.blob;
   sm.prof = (p.prof != nullptr && blockIdx.x == 0) ? p.prof : nullptr;
   prof_mark(sm.prof, 0);
-  // ---- phase 0: embeddings (one batch row per CTA) + L2 prefetch of layer 0 ----
+  // ---- phase 0: embeddings + L2 prefetch of layer 0 ----
   if (tid == 0) {
     const char* lb = blob + p.layer0;
     prefetch_slice(lb + p.wqkv, p.qkv_rows, H, p.nt_qkv);
@@ -373,10 +378,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
     prefetch_slice(lb + p.fc1, p.F, H, p.nt_fc1);
     prefetch_slice(lb + p.fc2, H, p.F, p.nt_h);
   }
-  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+  {
     const bf16* tables = reinterpret_cast<const bf16*>(blob + p.embed);
     const bf16* postab = p.rope ? nullptr : reinterpret_cast<const bf16*>(blob + p.pos);
-    for (int c = tid; c < H; c += ST_THREADS) {
+    const int cpr = (H + ST_THREADS - 1) / ST_THREADS;  // column chunks per row: (row, chunk) items spread over all CTAs
+    for (int it = blockIdx.x; it < p.B * cpr; it += gridDim.x) {
+      const int b = it / cpr, c = (it - b * cpr) * ST_THREADS + tid;
+      if (c >= H) continue;
       float ev[16];
 #pragma unroll
       for (int k = 0; k < 16; k++)  // all K gathers in flight, then the left-to-right rounded sum
@@ -400,8 +408,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
     sm.prof = (p.prof != nullptr && blockIdx.x == 0) ? p.prof + (size_t)(ph + 1) * 8 : nullptr;
     prof_mark(sm.prof, 0);
     const char* lb = blob + p.layer0 + p.layer_stride * (l < p.L ? l : p.L - 1);
-    if (sub == 0) prefetch_kv(p, l, pos);
-    if (tid == ST_THREADS - 32) {
+    if (sub == 0 && !(p.dbg & 2)) prefetch_kv(p, l, pos);
+    if (tid == ST_THREADS - 32 && !(p.dbg & 1)) {
       // Pull the NEXT layer's weights into L2 while this layer runs, one matrix per phase (the matrix phase `sub`
       // of the next layer will use), so the HBM stream is spread over the layer instead of colliding with one
       // phase's activation staging.  LayerNorm parameters ride along (they would otherwise be cold HBM reads
