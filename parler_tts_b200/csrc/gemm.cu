@@ -47,7 +47,8 @@ constexpr int TILE_M = 32;
 template <int NT, int PF>
 __global__ void __launch_bounds__(GEMM_THREADS) linear_bf16_kernel(LinearArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float ln_stats[64];  // (mean, rstd) per row when LayerNorm is folded in
+  __shared__ float ln_stats[64];        // (mean, rstd) per row when LayerNorm is folded in
+  __shared__ float ln_part[8 * 32 * 2];  // per-warp partial (S1, S2), ln_stats.cuh
   bf16* xs = reinterpret_cast<bf16*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Kc = p.Kc, lds = Kc + 8;
@@ -84,6 +85,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) linear_bf16_kernel(LinearArgs p)
 #pragma unroll
       for (int e = 0; e < 4; e++) acc[a][j][e] = 0.f;
 
+  RowStatFrag rst;
+  row_stat_zero(rst);
   const bf16* __restrict__ X = reinterpret_cast<const bf16*>(p.X);
   for (int c = 0; c < n_chunks; c++) {
     if (c > 0) {
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) linear_bf16_kernel(LinearArgs p)
       *reinterpret_cast<uint4*>(xs + r * lds + cv * 8) = val;
     }
     __syncthreads();
-    if (p.c1 != nullptr) tile_row_stats(xs, lds, Kc, p.M - m0, p.eps, ln_stats);  // published by the barrier before the epilogue
+    if (p.c1 != nullptr) row_stat_pass(rst, xs, lds, kt_per_chunk, warp, lane);  // tensor-core row sums (ln_stats.cuh)
     const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;
     const int lcol = (lane >> 4) * 8;
     for (int i0 = 0; i0 < per_chunk; i0 += PF) {
@@ -130,7 +133,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) linear_bf16_kernel(LinearArgs p)
       }
     }
   }
+  if (p.c1 != nullptr) row_stat_store(rst, ln_part, warp, lane);
   __syncthreads();
+  if (p.c1 != nullptr) row_stat_finalize(ln_part, p.K, p.M - m0, p.eps, ln_stats);  // published by the barrier before the epilogue
   // cross-warp K reduction in fixed order, then epilogue
   float* red = reinterpret_cast<float*>(smem_raw);  // [8][32][8*NT]
   constexpr int FB = 8 * NT;

@@ -28,6 +28,7 @@ namespace ptts {
 
 constexpr int ST_THREADS = 256;
 constexpr int ST_WARPS = 8;
+constexpr int ST_HEADER = 512 + 8 * 32 * 2 * 4;  // mbarriers [0,256) | row stats [256,512) | stat partials [512,2560)
 
 // ---- PTX helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,6 +117,7 @@ __device__ __forceinline__ void prof_mark(long long* prof, int slot) {
 struct Smem {
   uint64_t* bars;   // [2] tile buffers
   float* stats;     // [64] (mean, rstd) per row of the staged tile
+  float* part;      // [8][32][2] per-warp partial row sums (ln_stats.cuh)
   bf16* tile0;      // activation tile buffers (tile_of(sm, buf)), row pitch = H + 8
   unsigned char* scratch;  // start of the tile region (aliased by the K-reduction buffer and by attention)
   uint32_t parity;  // bit i: parity to wait for on bars[i]
@@ -204,7 +206,12 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
       }
       if (fresh) wait_tile(sm, buf);
       if (c == 0) prof_mark(sm.prof, 1);
-      if (fresh && d.c1 != nullptr) tile_row_stats(tile_of(sm, buf), sm.pitch, Kc, M, p.eps, sm.stats);  // (mean, rstd) per row; read in the epilogue
+      if (fresh && d.c1 != nullptr) {  // row sums on the tensor cores (LN-fused GEMMs are single-chunk: K == H)
+        RowStatFrag rst;
+        row_stat_zero(rst);
+        row_stat_pass(rst, tile_of(sm, buf), sm.pitch, kt_per_chunk, warp, lane);
+        row_stat_store(rst, sm.part, warp, lane);
+      }
       if (c == 0) prof_mark(sm.prof, 2);
       const bf16* xs = tile_of(sm, buf);
       for (int i0 = 0; i0 < per_chunk; i0 += PF) {
@@ -235,6 +242,7 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
     }
     prof_mark(sm.prof, 3);
     __syncthreads();
+    if (fresh && d.c1 != nullptr) row_stat_finalize(sm.part, d.K, M, p.eps, sm.stats);  // (mean, rstd) per row; read in the epilogue
     float* red = reinterpret_cast<float*>(resident ? tile_of(sm, 1) : tile_of(sm, 0));  // [8][32][FB], in an idle tile buffer
     {
       const int g = lane >> 2, t = lane & 3;
@@ -344,7 +352,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
   Smem sm;
   sm.bars = reinterpret_cast<uint64_t*>(smem_raw);
   sm.stats = reinterpret_cast<float*>(smem_raw + 256);
-  sm.scratch = smem_raw + 512;
+  sm.part = reinterpret_cast<float*>(smem_raw + 512);
+  sm.scratch = smem_raw + ST_HEADER;
   sm.pitch = H + 8;
   sm.nbuf = p.nbuf;
   sm.tile0 = reinterpret_cast<bf16*>(sm.scratch);
@@ -511,7 +520,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
 
 // ---- host side ----------------------------------------------------------------------------------
 int step_smem_bytes(const StepParams& p) {
-  return (int)(512 + p.tile_region_bytes);
+  return (int)(ST_HEADER + p.tile_region_bytes);
 }
 
 int launch_decode_step(const StepParams& p, int grid, cudaStream_t st) {
