@@ -303,38 +303,38 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
 #pragma unroll
     for (int e = 0; e < 8; e++) acc[e] = 0.f;
 
-    // one block of up to CH keys whose K/V rows sit in shared memory at kb/vb (row stride 64)
-    auto process = [&](const T* kb, const T* vb, int t_first, int n) {
+    // One block of n <= CH keys whose K/V rows sit in shared memory at kb/vb (row stride 64); bit r of `mword` = key r is
+    // attendable.  Branch-free: rows >= n are clamped to row n-1 (valid data) and get probability 0 through a -inf score,
+    // so the 8 per-key chains of a lane group are independent and interleave (a divergent `if` per key serialised them).
+    auto process = [&](const T* kb, const T* vb, uint32_t mword, int n) {
       constexpr int PER = CH / 4;  // keys per 8-lane group
       float sloc[PER];
+#pragma unroll
+      for (int u = 0; u < PER; u++) {
+        const int r = u * 4 + grp, rc = r < n ? r : n - 1;
+        float kf[8];
+        load8(kb + rc * HD + d0, kf);
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; e++) s = fmaf(qv[e], kf[e], s);
+        sloc[u] = s;
+      }
+#pragma unroll
+      for (int u = 0; u < PER; u++) sloc[u] += __shfl_xor_sync(0xffffffffu, sloc[u], 1);
+#pragma unroll
+      for (int u = 0; u < PER; u++) sloc[u] += __shfl_xor_sync(0xffffffffu, sloc[u], 2);
+#pragma unroll
+      for (int u = 0; u < PER; u++) sloc[u] += __shfl_xor_sync(0xffffffffu, sloc[u], 4);
       float cmax = -INFINITY;
 #pragma unroll
       for (int u = 0; u < PER; u++) {
         const int r = u * 4 + grp;
-        float s = -INFINITY;
-        if (r < n) {
-          float kf[8];
-          load8(kb + r * HD + d0, kf);
-          s = 0.f;
-#pragma unroll
-          for (int e = 0; e < 8; e++) s = fmaf(qv[e], kf[e], s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (r < n) {
-          s *= p.scale;
-          const int t = t_first + r;
-          if (km != nullptr && t < p.mask_len && km[t] == 0) s = -INFINITY;
-        } else {
-          s = -INFINITY;
-        }
-        sloc[u] = s;
-        cmax = fmaxf(cmax, s);
+        sloc[u] = (r < n && ((mword >> r) & 1u)) ? sloc[u] * p.scale : -INFINITY;
+        cmax = fmaxf(cmax, sloc[u]);
       }
       cmax = warp_max(cmax);
       const float m_new = fmaxf(m_run, cmax);
-      if (m_new == -INFINITY) return;  // every key so far is masked: nothing to accumulate
+      if (m_new == -INFINITY) return;  // every key so far is masked: nothing to accumulate (warp-uniform)
       const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
       l_run *= corr;
 #pragma unroll
@@ -342,22 +342,25 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
       float lsum = 0.f;
 #pragma unroll
       for (int u = 0; u < PER; u++) {
-        const int r = u * 4 + grp;
-        if (r < n && sloc[u] != -INFINITY) {
-          const float pe = expf(sloc[u] - m_new);
-          lsum += pe;  // identical on the 8 lanes of the group; counted once below
-          const float pw = DT<T>::rnd(pe);
-          float vf[8];
-          load8(vb + r * HD + d0, vf);
+        const int r = u * 4 + grp, rc = r < n ? r : n - 1;
+        const float pe = expf(sloc[u] - m_new);  // exactly 0 for a masked / out-of-range key
+        lsum += pe;  // identical on the 8 lanes of the group; counted once below
+        const float pw = DT<T>::rnd(pe);
+        float vf[8];
+        load8(vb + rc * HD + d0, vf);
 #pragma unroll
-          for (int e = 0; e < 8; e++) acc[e] = fmaf(pw, vf[e], acc[e]);
-        }
+        for (int e = 0; e < 8; e++) acc[e] = fmaf(pw, vf[e], acc[e]);
       }
       // sum of probabilities over the 4 groups (each group's 8 lanes hold the same value)
       lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
       lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
       l_run += lsum;
       m_run = m_new;
+    };
+    // attendable-key bits of the chunk starting at key t0 (the loads are issued before the wait on the chunk's TMA stage)
+    auto mask_bits = [&](int t0) -> int {
+      const int t = t0 + lane;
+      return (km != nullptr && lane < CH && t < p.mask_len && t < n_cached) ? km[t] : 1;
     };
 
     if (rr > 0) {  // GQA: further query heads re-stream the same cache rows
@@ -368,10 +371,11 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
     }
     for (int c = 0; c < n_chunks; c++) {
       const int st = c & 1;
-      wait_stage(st);
       const int t0 = (part + nparts * c) * CH;
       const int n = (n_cached - t0 < CH) ? (n_cached - t0) : CH;
-      process(kst + st * STAGE_ELEMS, vst + st * STAGE_ELEMS, t0, n);
+      const int mk = mask_bits(t0);
+      wait_stage(st);
+      process(kst + st * STAGE_ELEMS, vst + st * STAGE_ELEMS, __ballot_sync(0xffffffffu, mk != 0), n);
       if (c + 2 < n_chunks) {
         __syncwarp();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
