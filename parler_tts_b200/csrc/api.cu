@@ -235,7 +235,7 @@ static bool setup_fused(ptts_session* s) {
   p.c_qkv = L.c_qkv; p.c_qc = L.c_qc; p.c_fc1 = L.c_fc1; p.c_heads = L.c_heads;
   p.final_ln_w = L.final_ln_w; p.final_ln_b = L.final_ln_b; p.heads = L.heads; p.rope_cos = L.rope_cos; p.rope_sin = L.rope_sin;
   char* ws = s->ws;
-  p.x = (bf16*)(ws + W.x); p.qkv = (bf16*)(ws + W.qkv); p.attn = (bf16*)(ws + W.attn); p.qc = (bf16*)(ws + W.qc); p.hbuf = (bf16*)(ws + W.hbuf);
+  p.x = (bf16*)(ws + W.img_x); p.qkv = (bf16*)(ws + W.qkv); p.attn = (bf16*)(ws + W.img_attn); p.qc = (bf16*)(ws + W.qc); p.hbuf = (bf16*)(ws + W.img_h);
   p.logits = (float*)(ws + W.logits);
   p.cross_kv = ws + W.cross_kv; p.cross_layer_stride = W.cross_layer_stride;
   p.self_kv = ws + W.self_kv; p.self_layer_stride = W.self_layer_stride;

@@ -107,6 +107,7 @@ struct WorkspaceLayout {
   int B, P, S, Tmax, Mmax, BK;
   int64_t ctrl, progress, gen, raw_ids, cur_ids, eos_seen, unfinished, first_unf, prompt_mask, enc_mask;
   int64_t x, qkv, attn, qc, hbuf, hidden, logits, scores, cross_tmp, cross_kv, self_kv;
+  int64_t img_x, img_attn, img_h;  // fused step kernel: activations as tile images [chunk][32][H + 8] (step.cu stage_tile)
   int64_t cross_layer_stride, self_layer_stride;  // bytes
   int64_t raw_ld;                                  // raw_ids leading dimension (elements)
   int64_t total;
@@ -137,6 +138,9 @@ static inline WorkspaceLayout make_workspace(const ptts_decoder_config& c, int B
   w.qc = take((int64_t)w.Mmax * l.H * l.es);
   w.hbuf = take((int64_t)w.Mmax * l.F * l.es);
   w.hidden = take((int64_t)B * l.H * l.es);
+  w.img_x = take((int64_t)32 * (l.H + 8) * 2);
+  w.img_attn = take((int64_t)32 * (l.H + 8) * 2);
+  w.img_h = take((int64_t)((l.F + l.H - 1) / l.H) * 32 * (l.H + 8) * 2);
   w.logits = take((int64_t)w.BK * l.V * 4);
   w.scores = take((int64_t)w.BK * l.V * 4);
   w.cross_layer_stride = align_up(rows_enc * l.ckv_rows * l.es, 256);

@@ -128,17 +128,18 @@ struct Smem {
 
 __device__ __forceinline__ bf16* tile_of(const Smem& sm, int buf) { return sm.tile0 + (size_t)buf * 32 * sm.pitch; }
 
-// TMA-stage x[0:M, col0:col0+Kc] into tile buffer `buf` (called by all threads).
-__device__ __forceinline__ void stage_tile(Smem& sm, int buf, const bf16* X, int64_t ldx, int col0, int Kc, int M) {
-  __syncthreads();  // every generic-proxy access to the buffer (ldmatrix, LN, reduction scratch) is done
-  if (threadIdx.x < 32) {
+// TMA-stage one K-chunk of the activations into tile buffer `buf` (called by all threads).  The fused kernel keeps its
+// transient activations in global memory as TILE IMAGES: [chunk][32 rows][H + 8] with the shared-memory row pitch, so a
+// chunk is ONE contiguous bulk copy.  (The TMA front end takes ~29 ns per cp.async.bulk: 32 per-row copies cost 0.95 us
+// of issue time on the critical path of every GEMM phase; tools/ubench.cu, profiles/r01_step_phases.md.)
+__device__ __forceinline__ void stage_tile(Smem& sm, int buf, const bf16* img, int M, bool mark) {
+  __syncthreads();  // every generic-proxy access to the buffer (ldmatrix, reduction scratch) is done
+  if (threadIdx.x == 0) {
     fence_proxy_async();
-    if (threadIdx.x == 0) mbar_expect_tx(&sm.bars[buf], (uint32_t)(M * Kc * 2));
-    __syncwarp();
-    // one bulk copy per row (tools/ubench.cu: 1.23 us for the 64 KB tile with all 148 CTAs reading the same
-    // lines -- no L2 hot-spotting; splitting rows into more, staggered copies was 3x slower: per-copy cost)
-    if ((int)threadIdx.x < M)
-      bulk_g2s(tile_of(sm, buf) + (size_t)threadIdx.x * sm.pitch, X + (size_t)threadIdx.x * ldx + col0, (uint32_t)(Kc * 2), &sm.bars[buf]);
+    const uint32_t bytes = (uint32_t)(M * sm.pitch * 2);
+    mbar_expect_tx(&sm.bars[buf], bytes);
+    bulk_g2s(tile_of(sm, buf), img, bytes, &sm.bars[buf]);
+    if (mark) prof_mark(sm.prof, 5);  // copy issued
   }
 }
 __device__ __forceinline__ void wait_tile(Smem& sm, int buf) {
@@ -146,15 +147,66 @@ __device__ __forceinline__ void wait_tile(Smem& sm, int buf) {
   sm.parity ^= (1u << buf);
 }
 
+// L2 prefetch job issued by one thread right after the CTA's first tile copy (never before: fence.proxy.async waits
+// for outstanding bulk operations of the CTA, prefetches included)
+struct PrefetchJob {
+  const char* w; int N, K, nt;       // this CTA's weight slices of a [N][K] matrix packed with nt n-tiles per task (nullptr = none)
+  const char* v; uint32_t v_bytes;   // folded-LayerNorm vectors riding along (nullptr = none)
+  int kv_layer, pos;                 // kv_layer >= 0: also prefetch this layer's K/V rows up to cache position pos (warps 4-7)
+};
+
 struct GemmDesc {
-  const bf16* X; int64_t ldx;
+  const bf16* X; int64_t x_chunk_stride;  // activation tile images: chunk c (H columns) at X + c * x_chunk_stride
   const uint4* W;
   int N, K;
   const float* c1; const float* c2;  // folded LayerNorm vectors (ln_stats.cuh) or nullptr
   int epi;
   const bf16* R;
   void* Y; int64_t ldy;
+  int y_chunk; int64_t y_chunk_stride;  // feature n of row r lives at (n / y_chunk) * y_chunk_stride + r * ldy + n % y_chunk
+  PrefetchJob pf;
 };
+
+// bytes of this CTA's weight slice for a GEMM (first task only) -> L2, one layer ahead
+__device__ __forceinline__ void prefetch_slice(const char* w, int N, int K, int nt) {
+  const int ntasks = N / (8 * nt);
+  for (int task = blockIdx.x; task < ntasks; task += gridDim.x)
+    l2_prefetch(w + (size_t)task * nt * K * 16, (uint32_t)(nt * K * 16));
+}
+
+// L2 prefetch of the K/V rows this CTA's warps will read in the coming attention phases of layer l.
+__device__ __forceinline__ void prefetch_kv(const StepParams& p, int l, int pos) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < 4) return;  // warps 0-3 go straight to the GEMM (warp 0 issues its TMA tile copies)
+  const int pw = warp - 4;  // 4 prefetching warps cover the CTA's items
+  if (pos > 0 && lane == 0) {
+    const char* kc = p.self_kv + p.self_layer_stride * l;
+    const size_t vofs = (size_t)p.B * p.nkv * p.Tmax * HD * 2;
+    for (int it = blockIdx.x + gridDim.x * pw; it < p.B * p.nkv; it += gridDim.x * 4) {  // (any warp may prefetch any item)
+      const char* k = kc + (size_t)it * p.Tmax * HD * 2;  // [B][nkv][Tmax][64]: item-major
+      l2_prefetch(k, (uint32_t)(pos * HD * 2));
+      l2_prefetch(k + vofs, (uint32_t)(pos * HD * 2));
+    }
+  }
+  if (lane == 0) {  // cross K/V of this CTA's items (item-major, contiguous)
+    const char* ck = p.cross_kv + p.cross_layer_stride * l;
+    const size_t vofs = (size_t)p.B * p.nckv * p.S * HD * 2;
+    for (int it = blockIdx.x + gridDim.x * pw; it < p.B * p.nckv; it += gridDim.x * 4) {
+      const char* k = ck + (size_t)it * p.S * HD * 2;
+      l2_prefetch(k, (uint32_t)(p.S * HD * 2));
+      l2_prefetch(k + vofs, (uint32_t)(p.S * HD * 2));
+    }
+  }
+}
+
+__device__ __forceinline__ void issue_prefetch(const StepParams& p, const PrefetchJob& j) {
+  if (p.dbg & 1) return;
+  if (j.kv_layer >= 0 && !(p.dbg & 2)) prefetch_kv(p, j.kv_layer, j.pos);
+  if (threadIdx.x == ST_THREADS - 32) {
+    if (j.w != nullptr) prefetch_slice(j.w, j.N, j.K, j.nt);
+    if (j.v != nullptr) l2_prefetch(j.v, j.v_bytes);
+  }
+}
 
 // All tasks (n-blocks of 8*NT features) of one linear layer assigned to this CTA.  M = B <= 32 rows.
 template <int NT, int PF>
@@ -181,11 +233,12 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
     };
     // activations first (they are the critical path: the weights are already L2-resident), chunk 0 and, when
     // double-buffered, chunk 1; then the first PF weight slabs of this warp
-    if (fresh) stage_tile(sm, 0, d.X, d.ldx, 0, Kc, M);
-    if (sm.nbuf > 1 && n_chunks > 1) stage_tile(sm, 1, d.X, d.ldx, Kc, Kc, M);
+    if (fresh) stage_tile(sm, 0, d.X, M, true);
+    if (sm.nbuf > 1 && n_chunks > 1) stage_tile(sm, 1, d.X + d.x_chunk_stride, M, false);
 #pragma unroll
     for (int s = 0; s < PF; s++)
       if (s < per_chunk) load_w(wr[s], 0, s);
+    if (task == (int)blockIdx.x) issue_prefetch(p, d.pf);  // next layer's weights / this layer's K/V -> L2, off the critical path
     float acc[2][NT][4];
 #pragma unroll
     for (int a = 0; a < 2; a++)
@@ -202,7 +255,7 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
 #pragma unroll
         for (int s = 0; s < PF; s++)
           if (s < per_chunk) load_w(wr[s], c, s);
-        if (sm.nbuf == 1) stage_tile(sm, 0, d.X, d.ldx, c * Kc, Kc, M);
+        if (sm.nbuf == 1) stage_tile(sm, 0, d.X + c * d.x_chunk_stride, M, false);
       }
       if (fresh) wait_tile(sm, buf);
       if (c == 0) prof_mark(sm.prof, 1);
@@ -238,7 +291,7 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
           }
         }
       }
-      if (sm.nbuf > 1 && c + 2 < n_chunks) stage_tile(sm, buf, d.X, d.ldx, (c + 2) * Kc, Kc, M);
+      if (sm.nbuf > 1 && c + 2 < n_chunks) stage_tile(sm, buf, d.X + (c + 2) * d.x_chunk_stride, M, false);
     }
     prof_mark(sm.prof, 3);
     __syncthreads();
@@ -267,7 +320,8 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
       for (int w = 0; w < ST_WARPS; w++) v += red[((size_t)w * 32 + r) * FB + cidx];
       if (d.c1 != nullptr) v = sm.stats[2 * r + 1] * (v - sm.stats[2 * r] * d.c1[n0 + cidx]) + d.c2[n0 + cidx];
       v = DT<bf16>::rnd(v);
-      const size_t yo = (size_t)r * d.ldy + n0 + cidx;
+      const int n = n0 + cidx, yc = n / d.y_chunk;
+      const size_t yo = (size_t)yc * d.y_chunk_stride + (size_t)r * d.ldy + (n - yc * d.y_chunk);
       if (d.epi == EPI_ACT) v = apply_act(v, p.act);
       else if (d.epi == EPI_RESIDUAL) v = DT<bf16>::to_f(d.R[yo]) + v;
       if (d.epi == EPI_F32) reinterpret_cast<float*>(d.Y)[yo] = v;
@@ -286,13 +340,6 @@ __device__ __forceinline__ void run_gemm(const StepParams& p, Smem& sm, const Ge
   }
 }
 
-// bytes of this CTA's weight slice for a GEMM (first task only) -> L2, one layer ahead
-__device__ __forceinline__ void prefetch_slice(const char* w, int N, int K, int nt) {
-  const int ntasks = N / (8 * nt);
-  for (int task = blockIdx.x; task < ntasks; task += gridDim.x)
-    l2_prefetch(w + (size_t)task * nt * K * 16, (uint32_t)(nt * K * 16));
-}
-
 // Attention phase: one warp per (batch row, kv head) item, TMA-staged K/V.  Items are dealt round-robin over
 // CTAs first (item i -> CTA i % grid, warp i / grid) so all 148 SMs pull K/V, 3-4 warps each at Mini/B=32.
 __device__ __forceinline__ void attn_phase(const StepParams& p, Smem& sm, const AttnArgs& a, int nkv, int pos, uint32_t& att_parity) {
@@ -305,31 +352,6 @@ __device__ __forceinline__ void attn_phase(const StepParams& p, Smem& sm, const 
   __syncthreads();  // the tile / reduction scratch of the previous GEMM phase is dead
   for (int it = blockIdx.x + gridDim.x * pair; it < items; it += gridDim.x * (ST_WARPS / 2))
     attention_decode_item_warp<bf16>(a, it / nkv, it % nkv, pos, region, bars, lane, att_parity, part, 2, xch, pair + 1);
-}
-
-// L2 prefetch of the K/V rows this CTA's warps will read in the coming attention phases of layer l.
-__device__ __forceinline__ void prefetch_kv(const StepParams& p, int l, int pos) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < 4) return;  // warps 0-3 go straight to the GEMM (warp 0 issues its TMA tile copies)
-  const int pw = warp - 4;  // 4 prefetching warps cover the CTA's items
-  if (pos > 0 && lane == 0) {
-    const char* kc = p.self_kv + p.self_layer_stride * l;
-    const size_t vofs = (size_t)p.B * p.nkv * p.Tmax * HD * 2;
-    for (int it = blockIdx.x + gridDim.x * pw; it < p.B * p.nkv; it += gridDim.x * 4) {  // (any warp may prefetch any item)
-      const char* k = kc + (size_t)it * p.Tmax * HD * 2;  // [B][nkv][Tmax][64]: item-major
-      l2_prefetch(k, (uint32_t)(pos * HD * 2));
-      l2_prefetch(k + vofs, (uint32_t)(pos * HD * 2));
-    }
-  }
-  if (lane == 0) {  // cross K/V of this CTA's items (item-major, contiguous)
-    const char* ck = p.cross_kv + p.cross_layer_stride * l;
-    const size_t vofs = (size_t)p.B * p.nckv * p.S * HD * 2;
-    for (int it = blockIdx.x + gridDim.x * pw; it < p.B * p.nckv; it += gridDim.x * 4) {
-      const char* k = ck + (size_t)it * p.S * HD * 2;
-      l2_prefetch(k, (uint32_t)(p.S * HD * 2));
-      l2_prefetch(k + vofs, (uint32_t)(p.S * HD * 2));
-    }
-  }
 }
 
 template <int ITEMS>
@@ -403,7 +425,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
       for (int k = 0; k < 16; k++)
         if (k < p.K) v = (k == 0) ? ev[k] : DT<bf16>::rnd(v + ev[k]);
       if (postab != nullptr) v = DT<bf16>::rnd(v + __bfloat162float(postab[(size_t)pos * H + c]));
-      p.x[(size_t)b * H + c] = __float2bfloat16_rn(v);
+      p.x[(size_t)b * sm.pitch + c] = __float2bfloat16_rn(v);
     }
   }
   prof_mark(sm.prof, 6);
@@ -417,30 +439,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
     sm.prof = (p.prof != nullptr && blockIdx.x == 0) ? p.prof + (size_t)(ph + 1) * 8 : nullptr;
     prof_mark(sm.prof, 0);
     const char* lb = blob + p.layer0 + p.layer_stride * (l < p.L ? l : p.L - 1);
-    if (sub == 0 && !(p.dbg & 2)) prefetch_kv(p, l, pos);
-    if (tid == ST_THREADS - 32 && !(p.dbg & 1)) {
-      // Pull the NEXT layer's weights into L2 while this layer runs, one matrix per phase (the matrix phase `sub`
-      // of the next layer will use), so the HBM stream is spread over the layer instead of colliding with one
-      // phase's activation staging.  LayerNorm parameters ride along (they would otherwise be cold HBM reads
-      // on the critical path of every LN-fused GEMM).
-      const bool last = (l + 1 >= p.L);
-      const char* nb = lb + p.layer_stride;
-      switch (sub) {
-        case 0:
-          if (!last) { prefetch_slice(nb + p.wqkv, p.qkv_rows, H, p.nt_qkv); l2_prefetch(nb + p.c_qkv, (uint32_t)p.qkv_rows * 8); }
-          else { prefetch_slice(blob + p.heads, p.K * p.V, H, p.nt_heads); l2_prefetch(blob + p.c_heads, (uint32_t)(p.K * p.V) * 8); }
-          break;
-        case 2: if (!last) prefetch_slice(nb + p.wo, H, H, p.nt_h); break;
-        case 3: if (!last) { prefetch_slice(nb + p.wqc, H, H, p.nt_h); l2_prefetch(nb + p.c_qc, (uint32_t)H * 8); } break;
-        case 5: if (!last) prefetch_slice(nb + p.woc, H, H, p.nt_h); break;
-        case 6: if (!last) { prefetch_slice(nb + p.fc1, p.F, H, p.nt_fc1); l2_prefetch(nb + p.c_fc1, (uint32_t)p.F * 8); } break;
-        case 7: if (!last) prefetch_slice(nb + p.fc2, H, p.F, p.nt_h); break;
-        default: break;
-      }
-    }
     if (sub == 1 || sub == 4) {
       AttnArgs a{};
-      a.ldo = H; a.out = p.attn; a.ctrl = nullptr; a.B = p.B; a.nh = p.nh; a.q_len = 1;
+      a.ldo = sm.pitch; a.out = p.attn; a.ctrl = nullptr; a.B = p.B; a.nh = p.nh; a.q_len = 1;
       a.past_from_ctrl = 0; a.past_len = pos; a.prefix = p.P;
       a.rope = p.rope; a.rope_cos = blob + p.rope_cos; a.rope_sin = blob + p.rope_sin; a.scale = p.scale;
       if (sub == 1) {  // self-attention over the cache (+ append of the new K/V row)
@@ -461,35 +462,64 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
       }
       attn_phase(p, sm, a, a.nkv, pos, att_parity);
     } else {
+      // Activations live in tile images (row pitch H + 8, see stage_tile).  Each GEMM phase also pulls the matrix the
+      // SAME phase of the next layer will use into L2 (PrefetchJob), so the HBM stream is spread over the layer;
+      // folded-LayerNorm vectors ride along, and the qkv phase prefetches this layer's K/V rows.
+      const bool last = (l + 1 >= p.L);
+      const char* nb = lb + p.layer_stride;
+      const int64_t img = (int64_t)32 * sm.pitch;  // elements per tile image
+      const int ld = sm.pitch;
       GemmDesc g{};
+      g.y_chunk = 1 << 30; g.y_chunk_stride = 0; g.x_chunk_stride = img;
+      g.pf.w = nullptr; g.pf.v = nullptr; g.pf.kv_layer = -1; g.pf.pos = pos;
       int nt = p.nt_h;
+      auto set_pf = [&](int64_t w, int N, int K, int pnt, int64_t v, int vn) {
+        if (last) return;
+        g.pf.w = nb + w; g.pf.N = N; g.pf.K = K; g.pf.nt = pnt;
+        if (vn > 0) { g.pf.v = nb + v; g.pf.v_bytes = (uint32_t)vn * 8; }
+      };
       switch (sub) {
         case 0:  // qkv = LN1(x) Wqkv^T
-          g = GemmDesc{p.x, H, reinterpret_cast<const uint4*>(lb + p.wqkv), p.qkv_rows, H, reinterpret_cast<const float*>(lb + p.c_qkv),
-                       reinterpret_cast<const float*>(lb + p.c_qkv) + p.qkv_rows, EPI_STORE, nullptr, p.qkv, p.qkv_rows};
+          g.X = p.x; g.W = reinterpret_cast<const uint4*>(lb + p.wqkv); g.N = p.qkv_rows; g.K = H;
+          g.c1 = reinterpret_cast<const float*>(lb + p.c_qkv); g.c2 = g.c1 + p.qkv_rows;
+          g.epi = EPI_STORE; g.R = nullptr; g.Y = p.qkv; g.ldy = p.qkv_rows;
           nt = p.nt_qkv;
+          set_pf(p.wqkv, p.qkv_rows, H, p.nt_qkv, p.c_qkv, p.qkv_rows);
+          if (last) { g.pf.w = blob + p.heads; g.pf.N = p.K * p.V; g.pf.K = H; g.pf.nt = p.nt_heads; g.pf.v = blob + p.c_heads; g.pf.v_bytes = (uint32_t)(p.K * p.V) * 8; }
+          g.pf.kv_layer = l;
           break;
         case 2:  // x += attn Wo^T
-          g = GemmDesc{p.attn, H, reinterpret_cast<const uint4*>(lb + p.wo), H, H, nullptr, nullptr, EPI_RESIDUAL, p.x, p.x, H};
+          g.X = p.attn; g.W = reinterpret_cast<const uint4*>(lb + p.wo); g.N = H; g.K = H; g.c1 = nullptr; g.c2 = nullptr;
+          g.epi = EPI_RESIDUAL; g.R = p.x; g.Y = p.x; g.ldy = ld;
+          set_pf(p.wo, H, H, p.nt_h, 0, 0);
           break;
         case 3:  // q_cross = LN2(x) Wq^T
-          g = GemmDesc{p.x, H, reinterpret_cast<const uint4*>(lb + p.wqc), H, H, reinterpret_cast<const float*>(lb + p.c_qc),
-                       reinterpret_cast<const float*>(lb + p.c_qc) + H, EPI_STORE, nullptr, p.qc, H};
+          g.X = p.x; g.W = reinterpret_cast<const uint4*>(lb + p.wqc); g.N = H; g.K = H;
+          g.c1 = reinterpret_cast<const float*>(lb + p.c_qc); g.c2 = g.c1 + H;
+          g.epi = EPI_STORE; g.R = nullptr; g.Y = p.qc; g.ldy = H;
+          set_pf(p.wqc, H, H, p.nt_h, p.c_qc, H);
           break;
         case 5:  // x += attn Wo_cross^T
-          g = GemmDesc{p.attn, H, reinterpret_cast<const uint4*>(lb + p.woc), H, H, nullptr, nullptr, EPI_RESIDUAL, p.x, p.x, H};
+          g.X = p.attn; g.W = reinterpret_cast<const uint4*>(lb + p.woc); g.N = H; g.K = H; g.c1 = nullptr; g.c2 = nullptr;
+          g.epi = EPI_RESIDUAL; g.R = p.x; g.Y = p.x; g.ldy = ld;
+          set_pf(p.woc, H, H, p.nt_h, 0, 0);
           break;
-        case 6:  // h = act(LN3(x) W1^T)
-          g = GemmDesc{p.x, H, reinterpret_cast<const uint4*>(lb + p.fc1), p.F, H, reinterpret_cast<const float*>(lb + p.c_fc1),
-                       reinterpret_cast<const float*>(lb + p.c_fc1) + p.F, EPI_ACT, nullptr, p.hbuf, p.F};
+        case 6:  // h = act(LN3(x) W1^T), written as F/H tile images
+          g.X = p.x; g.W = reinterpret_cast<const uint4*>(lb + p.fc1); g.N = p.F; g.K = H;
+          g.c1 = reinterpret_cast<const float*>(lb + p.c_fc1); g.c2 = g.c1 + p.F;
+          g.epi = EPI_ACT; g.R = nullptr; g.Y = p.hbuf; g.ldy = ld; g.y_chunk = H; g.y_chunk_stride = img;
           nt = p.nt_fc1;
+          set_pf(p.fc1, p.F, H, p.nt_fc1, p.c_fc1, p.F);
           break;
         case 7:  // x += h W2^T
-          g = GemmDesc{p.hbuf, p.F, reinterpret_cast<const uint4*>(lb + p.fc2), H, p.F, nullptr, nullptr, EPI_RESIDUAL, p.x, p.x, H};
+          g.X = p.hbuf; g.W = reinterpret_cast<const uint4*>(lb + p.fc2); g.N = H; g.K = p.F; g.c1 = nullptr; g.c2 = nullptr;
+          g.epi = EPI_RESIDUAL; g.R = p.x; g.Y = p.x; g.ldy = ld;
+          set_pf(p.fc2, H, p.F, p.nt_h, 0, 0);
           break;
         default:  // final LayerNorm + K lm heads -> f32 logits [B, K*V]
-          g = GemmDesc{p.x, H, reinterpret_cast<const uint4*>(blob + p.heads), p.K * p.V, H, reinterpret_cast<const float*>(blob + p.c_heads),
-                       reinterpret_cast<const float*>(blob + p.c_heads) + p.K * p.V, EPI_F32, nullptr, p.logits, (int64_t)p.K * p.V};
+          g.X = p.x; g.W = reinterpret_cast<const uint4*>(blob + p.heads); g.N = p.K * p.V; g.K = H;
+          g.c1 = reinterpret_cast<const float*>(blob + p.c_heads); g.c2 = g.c1 + p.K * p.V;
+          g.epi = EPI_F32; g.R = nullptr; g.Y = p.logits; g.ldy = (int64_t)p.K * p.V;
           nt = p.nt_heads;
           break;
       }

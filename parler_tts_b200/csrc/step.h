@@ -15,7 +15,7 @@ struct StepParams {
   int64_t c_qkv, c_qc, c_fc1, c_heads;   // folded-LayerNorm vectors
   int64_t final_ln_w, final_ln_b, heads, rope_cos, rope_sin;
   // workspace
-  bf16 *x, *qkv, *attn, *qc, *hbuf;
+  bf16 *x, *qkv, *attn, *qc, *hbuf;  // x / attn / hbuf are tile images (row pitch H + 8; hbuf: F/H images), qkv / qc plain rows
   float* logits;
   char* cross_kv; int64_t cross_layer_stride;
   char* self_kv; int64_t self_layer_stride;

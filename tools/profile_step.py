@@ -47,13 +47,13 @@ for ph in range(1, 8 * 24 + 1):
     r = t[ph]
     work = (r[6] - r[0]) / ghz / 1e3
     barr = (r[7] - r[6]) / ghz / 1e3
-    parts = [(r[1] - r[0]), (r[2] - r[1]), (r[3] - r[2]), (r[4] - r[3]), ((r[5] - r[1]) if r[5] > 0 else 0)] if sub not in (1, 4) else [0, 0, 0, 0, 0]
+    parts = [(r[1] - r[0]), (r[2] - r[1]), (r[3] - r[2]), (r[4] - r[3]), ((r[5] - r[0]) if r[5] > 0 else 0)] if sub not in (1, 4) else [0, 0, 0, 0, 0]
     agg.setdefault(sub, []).append([work, barr] + [x / ghz / 1e3 for x in parts])
 out = {}
 for sub, v in agg.items():
     m = np.array(v).mean(0)
     out[names[sub]] = [round(float(x), 2) for x in m]
-    print(f"{names[sub]:12s} work {m[0]:6.2f}  barrier {m[1]:6.2f} | tile {m[2]:6.2f}  ln {m[3]:6.2f} (of which sync/lnp {m[6]:5.2f})  mma {m[4]:6.2f}  epi {m[5]:6.2f}")
+    print(f"{names[sub]:12s} work {m[0]:6.2f}  barrier {m[1]:6.2f} | tile {m[2]:6.2f}  ln {m[3]:6.2f} (issued at {m[6]:5.2f})  mma {m[4]:6.2f}  epi {m[5]:6.2f}")
 r = t[0]
 print(f"embed work {(r[6]-r[0])/ghz/1e3:.2f} barrier {(r[7]-r[6])/ghz/1e3:.2f}")
 r = t[8 * 24 + 1]
