@@ -255,11 +255,9 @@ static bool setup_fused(ptts_session* s) {
   if (p.nt_heads > ntmax) ntmax = p.nt_heads;
   const int64_t tile = (int64_t)32 * (L.H + 8) * 2;
   const int64_t red = (int64_t)8 * 32 * 8 * ntmax * 4;
-  int kvcap = W.Tmax > W.S ? W.Tmax : W.S;
-  (void)kvcap;
   p.attn_floats_per_warp = 0;
   const int64_t att = (int64_t)8 * (2 * 2 * 32 * 64 * 2 + 3 * 64 * 4) + 4 * 128 * 4;  // 8 x attn_decode_smem_per_warp<bf16>() + pair exchange
-  const int64_t budget = 215 * 1024 - 2560;  // step.cu ST_HEADER
+  const int64_t budget = 215 * 1024 - 2816;  // step.cu ST_HEADER
   p.nbuf = (2 * tile <= budget) ? 2 : 1;
   int64_t region = p.nbuf * tile;
   if (red > region) region = red;

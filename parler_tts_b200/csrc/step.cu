@@ -28,7 +28,7 @@ namespace ptts {
 
 constexpr int ST_THREADS = 256;
 constexpr int ST_WARPS = 8;
-constexpr int ST_HEADER = 512 + 8 * 32 * 2 * 4;  // mbarriers [0,256) | row stats [256,512) | stat partials [512,2560)
+constexpr int ST_HEADER = 512 + 8 * 32 * 2 * 4 + 256;  // mbarriers [0,256) | row stats [256,512) | stat partials [512,2560) | c1,c2 of the task [2560,2816)
 
 // ---- PTX helpers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,6 +91,9 @@ __device__ __forceinline__ uint4 ldg_stream_s(const uint4* p) {
 // RELAXED load (an acquire load would invalidate L1 on every poll); one acquire fence after the exit.
 __device__ __forceinline__ unsigned grid_sync(unsigned* ctr, unsigned target, int* progress = nullptr, int ph = 0) {
   target += gridDim.x;
+  // this thread's global writes (generic proxy) -> later TMA reads by other CTAs (async proxy): the proxy fence sits on the
+  // writer side of the release/acquire chain, where it overlaps the store drain instead of delaying the next tile copy
+  asm volatile("fence.proxy.async.global;" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 0) {
     if (progress) progress[blockIdx.x] = ph;
@@ -118,6 +121,7 @@ struct Smem {
   uint64_t* bars;   // [2] tile buffers
   float* stats;     // [64] (mean, rstd) per row of the staged tile
   float* part;      // [8][32][2] per-warp partial row sums (ln_stats.cuh)
+  float* cvec;      // [2][32] folded-LN vectors c1, c2 of the current task's features
   bf16* tile0;      // activation tile buffers (tile_of(sm, buf)), row pitch = H + 8
   unsigned char* scratch;  // start of the tile region (aliased by the K-reduction buffer and by attention)
   uint32_t parity;  // bit i: parity to wait for on bars[i]
@@ -135,7 +139,7 @@ __device__ __forceinline__ bf16* tile_of(const Smem& sm, int buf) { return sm.ti
 __device__ __forceinline__ void stage_tile(Smem& sm, int buf, const bf16* img, int M, bool mark) {
   __syncthreads();  // every generic-proxy access to the buffer (ldmatrix, reduction scratch) is done
   if (threadIdx.x == 0) {
-    fence_proxy_async();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // tile buffer: generic accesses (above barrier) before the async write
     const uint32_t bytes = (uint32_t)(M * sm.pitch * 2);
     mbar_expect_tx(&sm.bars[buf], bytes);
     bulk_g2s(tile_of(sm, buf), img, bytes, &sm.bars[buf]);
@@ -238,6 +242,8 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
 #pragma unroll
     for (int s = 0; s < PF; s++)
       if (s < per_chunk) load_w(wr[s], 0, s);
+    if (d.c1 != nullptr && threadIdx.x < 2 * FB)  // this task's c1 | c2 -> shared memory (read in the epilogue, two barriers later)
+      sm.cvec[(threadIdx.x < FB ? 0 : 32) + (threadIdx.x % FB)] = (threadIdx.x < FB ? d.c1 : d.c2)[nt0 * 8 + threadIdx.x % FB];
     if (task == (int)blockIdx.x) issue_prefetch(p, d.pf);  // next layer's weights / this layer's K/V -> L2, off the critical path
     float acc[2][NT][4];
 #pragma unroll
@@ -294,6 +300,13 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
       if (sm.nbuf > 1 && c + 2 < n_chunks) stage_tile(sm, buf, d.X + (c + 2) * d.x_chunk_stride, M, false);
     }
     prof_mark(sm.prof, 3);
+    const int n0 = nt0 * 8;
+    auto y_offset = [&](int r, int n) -> size_t {
+      const int yc = n / d.y_chunk;
+      return (size_t)yc * d.y_chunk_stride + (size_t)r * d.ldy + (n - yc * d.y_chunk);
+    };
+    float rv0 = 0.f;  // residual of this thread's first output, requested now: its L2 latency overlaps the K reduction
+    if (d.epi == EPI_RESIDUAL && (int)threadIdx.x / FB < M) rv0 = DT<bf16>::to_f(d.R[y_offset(threadIdx.x / FB, n0 + threadIdx.x % FB)]);
     __syncthreads();
     if (fresh && d.c1 != nullptr) row_stat_finalize(sm.part, d.K, M, p.eps, sm.stats);  // (mean, rstd) per row; read in the epilogue
     float* red = reinterpret_cast<float*>(resident ? tile_of(sm, 1) : tile_of(sm, 0));  // [8][32][FB], in an idle tile buffer
@@ -311,19 +324,17 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
         }
     }
     __syncthreads();
-    const int n0 = nt0 * 8;
     for (int o = threadIdx.x; o < 32 * FB; o += ST_THREADS) {
       const int r = o / FB, cidx = o - r * FB;
       if (r >= M) continue;
       float v = 0.f;
 #pragma unroll
       for (int w = 0; w < ST_WARPS; w++) v += red[((size_t)w * 32 + r) * FB + cidx];
-      if (d.c1 != nullptr) v = sm.stats[2 * r + 1] * (v - sm.stats[2 * r] * d.c1[n0 + cidx]) + d.c2[n0 + cidx];
+      if (d.c1 != nullptr) v = sm.stats[2 * r + 1] * (v - sm.stats[2 * r] * sm.cvec[cidx]) + sm.cvec[32 + cidx];
       v = DT<bf16>::rnd(v);
-      const int n = n0 + cidx, yc = n / d.y_chunk;
-      const size_t yo = (size_t)yc * d.y_chunk_stride + (size_t)r * d.ldy + (n - yc * d.y_chunk);
       if (d.epi == EPI_ACT) v = apply_act(v, p.act);
-      else if (d.epi == EPI_RESIDUAL) v = DT<bf16>::to_f(d.R[yo]) + v;
+      const size_t yo = y_offset(r, n0 + cidx);
+      if (d.epi == EPI_RESIDUAL) v = (o == (int)threadIdx.x ? rv0 : DT<bf16>::to_f(d.R[yo])) + v;
       if (d.epi == EPI_F32) reinterpret_cast<float*>(d.Y)[yo] = v;
       else reinterpret_cast<bf16*>(d.Y)[yo] = __float2bfloat16_rn(v);
     }
@@ -375,6 +386,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
   sm.bars = reinterpret_cast<uint64_t*>(smem_raw);
   sm.stats = reinterpret_cast<float*>(smem_raw + 256);
   sm.part = reinterpret_cast<float*>(smem_raw + 512);
+  sm.cvec = reinterpret_cast<float*>(smem_raw + 2560);
   sm.scratch = smem_raw + ST_HEADER;
   sm.pitch = H + 8;
   sm.nbuf = p.nbuf;
