@@ -255,15 +255,21 @@ static bool setup_fused(ptts_session* s) {
   if (p.nt_heads > ntmax) ntmax = p.nt_heads;
   const int64_t tile = (int64_t)32 * (L.H + 8) * 2;
   const int64_t red = (int64_t)8 * 32 * 8 * ntmax * 4;
+  // weight buffer: the largest per-task slice (nt n-tiles x K, 16 bytes per (n-tile, k-pair) fragment row)
+  int64_t wbytes = (int64_t)p.nt_qkv * L.H * 16;
+  if ((int64_t)p.nt_h * L.F * 16 > wbytes) wbytes = (int64_t)p.nt_h * L.F * 16;
+  if ((int64_t)p.nt_fc1 * L.H * 16 > wbytes) wbytes = (int64_t)p.nt_fc1 * L.H * 16;
+  if ((int64_t)p.nt_heads * L.H * 16 > wbytes) wbytes = (int64_t)p.nt_heads * L.H * 16;
   p.attn_floats_per_warp = 0;
   const int64_t att = (int64_t)8 * (2 * 2 * 32 * 64 * 2 + 3 * 64 * 4) + 4 * 128 * 4;  // 8 x attn_decode_smem_per_warp<bf16>() + pair exchange
   const int64_t budget = 215 * 1024 - 2816;  // step.cu ST_HEADER
-  p.nbuf = (2 * tile <= budget) ? 2 : 1;
-  int64_t region = p.nbuf * tile;
-  if (red > region) region = red;
+  p.nbuf = (2 * tile + wbytes <= budget) ? 2 : 1;
+  if (p.nbuf * tile < red) return false;
+  p.wbuf_offset = align_up(p.nbuf * tile, 128);
+  int64_t region = p.wbuf_offset + wbytes;
   if (att > region) region = att;
   region = align_up(region, 16);
-  if (region > budget) return false;  // e.g. very long caches: fall back to the multi-kernel path
+  if (region > budget) return false;  // does not fit: the multi-kernel path runs instead
   p.tile_region_bytes = region;
   p.sample_items = (L.V + 31) / 32;
   if (p.sample_items > 72) return false;

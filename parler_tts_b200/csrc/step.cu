@@ -122,9 +122,10 @@ struct Smem {
   float* stats;     // [64] (mean, rstd) per row of the staged tile
   float* part;      // [8][32][2] per-warp partial row sums (ln_stats.cuh)
   float* cvec;      // [2][32] folded-LN vectors c1, c2 of the current task's features
+  const uint4* wbuf; // this CTA's weight slice of the current (or next) GEMM task, staged by TMA (B-fragment order)
   bf16* tile0;      // activation tile buffers (tile_of(sm, buf)), row pitch = H + 8
   unsigned char* scratch;  // start of the tile region (aliased by the K-reduction buffer and by attention)
-  uint32_t parity;  // bit i: parity to wait for on bars[i]
+  uint32_t parity;  // bit i: parity to wait for on bars[i] (bit 2: the weight barrier)
   long long* prof;  // CTA 0 / thread 0 timestamps of the current phase (nullptr = off)
   int pitch;
   int nbuf;
@@ -146,8 +147,8 @@ __device__ __forceinline__ void stage_tile(Smem& sm, int buf, const bf16* img, i
     if (mark) prof_mark(sm.prof, 5);  // copy issued
   }
 }
-__device__ __forceinline__ void wait_tile(Smem& sm, int buf) {
-  mbar_wait(&sm.bars[buf], (sm.parity >> buf) & 1u);
+__device__ __forceinline__ void wait_tile(Smem& sm, int buf) {  // buf 0/1: activation tiles; 2: the weight buffer (bars[18])
+  mbar_wait(&sm.bars[buf == 2 ? 18 : buf], (sm.parity >> buf) & 1u);
   sm.parity ^= (1u << buf);
 }
 
@@ -169,6 +170,7 @@ struct GemmDesc {
   void* Y; int64_t ldy;
   int y_chunk; int64_t y_chunk_stride;  // feature n of row r lives at (n / y_chunk) * y_chunk_stride + r * ldy + n % y_chunk
   PrefetchJob pf;
+  int ph;  // phase index (weight staging of the next job)
 };
 
 // bytes of this CTA's weight slice for a GEMM (first task only) -> L2, one layer ahead
@@ -212,15 +214,52 @@ __device__ __forceinline__ void issue_prefetch(const StepParams& p, const Prefet
   }
 }
 
+// ---- weight staging -------------------------------------------------------------------------------
+// The weight slice of a GEMM task (NT n-tiles x K, contiguous in the packed layout) is ONE bulk copy into shared
+// memory, issued as soon as the buffer is free -- i.e. right after the previous task's MMA loop, a full phase before
+// it is needed -- so the weights cross HBM/L2 -> SM during the previous epilogue and the device-wide barrier instead of
+// on the critical path (registers could keep only ~32 KB of loads in flight per SM: 2-3 us for a 64 KB slice).
+constexpr int WBAR = 18;  // sm.bars index of the weight mbarrier (0,1: tiles; 2..17: attention rings)
+
+struct WeightJob { const char* src; uint32_t bytes; };
+
+// matrix of GEMM phase `ph` (not an attention phase): packed weights, N, K and n-tiles per task
+__device__ __forceinline__ void gemm_matrix(const StepParams& p, int ph, const char*& W, int& N, int& K, int& nt) {
+  const int l = ph >> 3, sub = (ph >= 8 * p.L) ? 8 : (ph & 7);
+  const char* lb = p.blob + p.layer0 + p.layer_stride * (l < p.L ? l : p.L - 1);
+  const int H = p.H;
+  switch (sub) {
+    case 0: W = lb + p.wqkv; N = p.qkv_rows; K = H; nt = p.nt_qkv; break;
+    case 2: W = lb + p.wo; N = H; K = H; nt = p.nt_h; break;
+    case 3: W = lb + p.wqc; N = H; K = H; nt = p.nt_h; break;
+    case 5: W = lb + p.woc; N = H; K = H; nt = p.nt_h; break;
+    case 6: W = lb + p.fc1; N = p.F; K = H; nt = p.nt_fc1; break;
+    case 7: W = lb + p.fc2; N = H; K = p.F; nt = p.nt_h; break;
+    default: W = p.blob + p.heads; N = p.K * p.V; K = H; nt = p.nt_heads; break;
+  }
+}
+
+// Called by all threads AFTER a __syncthreads() that retired every reader of the weight buffer.
+__device__ __forceinline__ void issue_weights(const StepParams& p, Smem& sm, int ph, int task) {
+  if (threadIdx.x != 0) return;
+  const char* W; int N, K, nt;
+  gemm_matrix(p, ph, W, N, K, nt);
+  if (task >= N / (8 * nt)) return;
+  const uint32_t bytes = (uint32_t)nt * (uint32_t)K * 16u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(&sm.bars[WBAR], bytes);
+  bulk_g2s(const_cast<uint4*>(sm.wbuf), W + (size_t)task * bytes, bytes, &sm.bars[WBAR]);
+}
+__device__ __forceinline__ bool is_attn_phase(const StepParams& p, int ph) { return ph < 8 * p.L && ((ph & 7) == 1 || (ph & 7) == 4); }
+
 // All tasks (n-blocks of 8*NT features) of one linear layer assigned to this CTA.  M = B <= 32 rows.
-template <int NT, int PF>
+template <int NT>
 __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const GemmDesc& d) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = p.B, H = p.H;
   const int Kc = d.K < H ? d.K : H;
   const int n_chunks = d.K / Kc;
   const int kt_per_chunk = Kc >> 5, KT = d.K >> 5;
-  const int per_chunk = (kt_per_chunk > warp) ? (kt_per_chunk - warp + ST_WARPS - 1) / ST_WARPS : 0;
   const int ntasks = d.N / (8 * NT);
   constexpr int FB = 8 * NT;
   // single-chunk GEMMs with two tile buffers keep the staged tile (and its row statistics) resident across this CTA's
@@ -229,19 +268,9 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
   for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
     const bool fresh = !resident || task == (int)blockIdx.x;
     const int nt0 = task * NT;
-    uint4 wr[PF][NT];
-    auto load_w = [&](uint4 (&dst)[NT], int c, int i) {
-      const int ktg = c * kt_per_chunk + warp + ST_WARPS * i;
-#pragma unroll
-      for (int j = 0; j < NT; j++) dst[j] = ldg_stream_s(d.W + ((size_t)(nt0 + j) * KT + ktg) * 32 + lane);
-    };
-    // activations first (they are the critical path: the weights are already L2-resident), chunk 0 and, when
-    // double-buffered, chunk 1; then the first PF weight slabs of this warp
+    // activations: chunk 0 and, when double-buffered, chunk 1 (the weights were requested a phase ago)
     if (fresh) stage_tile(sm, 0, d.X, M, true);
     if (sm.nbuf > 1 && n_chunks > 1) stage_tile(sm, 1, d.X + d.x_chunk_stride, M, false);
-#pragma unroll
-    for (int s = 0; s < PF; s++)
-      if (s < per_chunk) load_w(wr[s], 0, s);
     if (d.c1 != nullptr && threadIdx.x < 2 * FB)  // this task's c1 | c2 -> shared memory (read in the epilogue, two barriers later)
       sm.cvec[(threadIdx.x < FB ? 0 : 32) + (threadIdx.x % FB)] = (threadIdx.x < FB ? d.c1 : d.c2)[nt0 * 8 + threadIdx.x % FB];
     if (task == (int)blockIdx.x) issue_prefetch(p, d.pf);  // next layer's weights / this layer's K/V -> L2, off the critical path
@@ -257,12 +286,7 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
     const int lcol = (lane >> 4) * 8;
     for (int c = 0; c < n_chunks; c++) {
       const int buf = (sm.nbuf > 1) ? (c & 1) : 0;
-      if (c > 0) {
-#pragma unroll
-        for (int s = 0; s < PF; s++)
-          if (s < per_chunk) load_w(wr[s], c, s);
-        if (sm.nbuf == 1) stage_tile(sm, 0, d.X + c * d.x_chunk_stride, M, false);
-      }
+      if (c > 0 && sm.nbuf == 1) stage_tile(sm, 0, d.X + c * d.x_chunk_stride, M, false);
       if (fresh) wait_tile(sm, buf);
       if (c == 0) prof_mark(sm.prof, 1);
       if (fresh && d.c1 != nullptr) {  // row sums on the tensor cores (LN-fused GEMMs are single-chunk: K == H)
@@ -271,29 +295,27 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
         row_stat_pass(rst, tile_of(sm, buf), sm.pitch, kt_per_chunk, warp, lane);
         row_stat_store(rst, sm.part, warp, lane);
       }
-      if (c == 0) prof_mark(sm.prof, 2);
+      if (c == 0) {
+        prof_mark(sm.prof, 2);
+        wait_tile(sm, 2);  // this task's weights (bars[WBAR]: parity bit 2)
+      }
       const bf16* xs = tile_of(sm, buf);
-      for (int i0 = 0; i0 < per_chunk; i0 += PF) {
+      for (int kt = warp; kt < kt_per_chunk; kt += ST_WARPS) {  // K split over the 8 warps
+        const uint4* wk = sm.wbuf + ((size_t)(c * kt_per_chunk + kt)) * 32 + lane;
+        uint4 w[NT];
 #pragma unroll
-        for (int s = 0; s < PF; s++) {
-          const int i = i0 + s;
-          if (i < per_chunk) {
-            const int kt = warp + ST_WARPS * i;
-            uint32_t a[2][2][4];
+        for (int j = 0; j < NT; j++) w[j] = wk[(size_t)j * KT * 32];
+        uint32_t a[2][2][4];
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++)
+        for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-              for (int j = 0; j < 2; j++) ldmatrix_x4s(a[mt][j], xs + (size_t)(mt * 16 + lrow) * sm.pitch + kt * 32 + j * 16 + lcol);
+          for (int j = 0; j < 2; j++) ldmatrix_x4s(a[mt][j], xs + (size_t)(mt * 16 + lrow) * sm.pitch + kt * 32 + j * 16 + lcol);
 #pragma unroll
-            for (int j = 0; j < NT; j++) {
-              const uint4 w = wr[s][j];
+        for (int j = 0; j < NT; j++) {
 #pragma unroll
-              for (int mt = 0; mt < 2; mt++) {
-                mma_bf16s(acc[mt][j], a[mt][0], w.x, w.y);
-                mma_bf16s(acc[mt][j], a[mt][1], w.z, w.w);
-              }
-            }
-            if (i + PF < per_chunk) load_w(wr[s], c, i + PF);
+          for (int mt = 0; mt < 2; mt++) {
+            mma_bf16s(acc[mt][j], a[mt][0], w[j].x, w[j].y);
+            mma_bf16s(acc[mt][j], a[mt][1], w[j].z, w[j].w);
           }
         }
       }
@@ -308,6 +330,10 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
     float rv0 = 0.f;  // residual of this thread's first output, requested now: its L2 latency overlaps the K reduction
     if (d.epi == EPI_RESIDUAL && (int)threadIdx.x / FB < M) rv0 = DT<bf16>::to_f(d.R[y_offset(threadIdx.x / FB, n0 + threadIdx.x % FB)]);
     __syncthreads();
+    // the weight buffer is free: request the next job's slice (next task of this matrix, else the next phase's matrix;
+    // when an attention phase comes next its end issues the copy -- the buffer may alias attention scratch)
+    if (task + (int)gridDim.x < ntasks) issue_weights(p, sm, d.ph, task + gridDim.x);
+    else if (d.ph < 8 * p.L && !is_attn_phase(p, d.ph + 1)) issue_weights(p, sm, d.ph + 1, blockIdx.x);
     if (fresh && d.c1 != nullptr) row_stat_finalize(sm.part, d.K, M, p.eps, sm.stats);  // (mean, rstd) per row; read in the epilogue
     float* red = reinterpret_cast<float*>(resident ? tile_of(sm, 1) : tile_of(sm, 0));  // [8][32][FB], in an idle tile buffer
     {
@@ -340,20 +366,22 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
     }
     prof_mark(sm.prof, 4);
   }
+  // a CTA without a task in this matrix still has to request its slice of the next one
+  if ((int)blockIdx.x >= ntasks && d.ph < 8 * p.L && !is_attn_phase(p, d.ph + 1)) issue_weights(p, sm, d.ph + 1, blockIdx.x);
 }
 
 __device__ __forceinline__ void run_gemm(const StepParams& p, Smem& sm, const GemmDesc& d, int nt) {
-  switch (nt) {  // variant set chosen so the fused kernel compiles without register spills (254 regs)
-    case 1: gemm_tasks<1, 4>(p, sm, d); break;
-    case 2: gemm_tasks<2, 4>(p, sm, d); break;
-    case 3: gemm_tasks<3, 2>(p, sm, d); break;
-    default: gemm_tasks<4, 2>(p, sm, d); break;
+  switch (nt) {
+    case 1: gemm_tasks<1>(p, sm, d); break;
+    case 2: gemm_tasks<2>(p, sm, d); break;
+    case 3: gemm_tasks<3>(p, sm, d); break;
+    default: gemm_tasks<4>(p, sm, d); break;
   }
 }
 
 // Attention phase: one warp per (batch row, kv head) item, TMA-staged K/V.  Items are dealt round-robin over
 // CTAs first (item i -> CTA i % grid, warp i / grid) so all 148 SMs pull K/V, 3-4 warps each at Mini/B=32.
-__device__ __forceinline__ void attn_phase(const StepParams& p, Smem& sm, const AttnArgs& a, int nkv, int pos, uint32_t& att_parity) {
+__device__ __forceinline__ void attn_phase(const StepParams& p, Smem& sm, const AttnArgs& a, int nkv, int pos, uint32_t& att_parity, int ph) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* region = sm.scratch + (size_t)warp * attn_decode_smem_per_warp<bf16>();
   uint64_t* bars = sm.bars + 2 + 2 * warp;
@@ -363,6 +391,8 @@ __device__ __forceinline__ void attn_phase(const StepParams& p, Smem& sm, const 
   __syncthreads();  // the tile / reduction scratch of the previous GEMM phase is dead
   for (int it = blockIdx.x + gridDim.x * pair; it < items; it += gridDim.x * (ST_WARPS / 2))
     attention_decode_item_warp<bf16>(a, it / nkv, it % nkv, pos, region, bars, lane, att_parity, part, 2, xch, pair + 1);
+  __syncthreads();  // attention scratch is dead: the next GEMM's weight slice may land (it overlaps the device-wide barrier)
+  issue_weights(p, sm, ph + 1, blockIdx.x);
 }
 
 template <int ITEMS>
@@ -388,6 +418,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
   sm.part = reinterpret_cast<float*>(smem_raw + 512);
   sm.cvec = reinterpret_cast<float*>(smem_raw + 2560);
   sm.scratch = smem_raw + ST_HEADER;
+  sm.wbuf = reinterpret_cast<const uint4*>(smem_raw + ST_HEADER + p.wbuf_offset);
   sm.pitch = H + 8;
   sm.nbuf = p.nbuf;
   sm.tile0 = reinterpret_cast<bf16*>(sm.scratch);
@@ -396,6 +427,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
   if (tid == 0) {
     mbar_init(&sm.bars[0], 1);
     mbar_init(&sm.bars[1], 1);
+    mbar_init(&sm.bars[WBAR], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   attention_decode_init_warp(sm.bars + 2 + 2 * warp, lane);  // per-warp K/V ring barriers: header bytes [16, 144)
@@ -406,6 +438,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
   unsigned bar_target = 0u;
   if (blockIdx.x == 0 && tid == 0) p.bar[(gen + 1u) & 1u] = 0u;  // the counter the NEXT launch will use
   __syncthreads();
+  issue_weights(p, sm, 0, blockIdx.x);  // layer 0's qkv slice lands during the embedding phase
 
   const char* blob = p.blob;
   sm.prof = (p.prof != nullptr && blockIdx.x == 0) ? p.prof : nullptr;
@@ -472,7 +505,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
         a.key_mask = p.enc_mask; a.mask_len = p.S; a.mask_ld = p.S;
         a.nkv = p.nckv; a.cross = 1; a.kv_len = p.S; a.kv_capacity = p.S;
       }
-      attn_phase(p, sm, a, a.nkv, pos, att_parity);
+      attn_phase(p, sm, a, a.nkv, pos, att_parity, ph);
     } else {
       // Activations live in tile images (row pitch H + 8, see stage_tile).  Each GEMM phase also pulls the matrix the
       // SAME phase of the next layer will use into L2 (PrefetchJob), so the HBM stream is spread over the layer;
@@ -483,7 +516,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
       const int ld = sm.pitch;
       GemmDesc g{};
       g.y_chunk = 1 << 30; g.y_chunk_stride = 0; g.x_chunk_stride = img;
-      g.pf.w = nullptr; g.pf.v = nullptr; g.pf.kv_layer = -1; g.pf.pos = pos;
+      g.pf.w = nullptr; g.pf.v = nullptr; g.pf.kv_layer = -1; g.pf.pos = pos; g.ph = ph;
       int nt = p.nt_h;
       auto set_pf = [&](int64_t w, int N, int K, int pnt, int64_t v, int vn) {
         if (last) return;

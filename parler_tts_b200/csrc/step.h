@@ -27,7 +27,8 @@ struct StepParams {
   int nt_qkv, nt_h, nt_fc1, nt_heads;
   int nbuf;                // activation-tile buffers (2 = double-buffered K chunks)
   int attn_floats_per_warp;
-  int64_t tile_region_bytes;
+  int64_t tile_region_bytes;   // scratch after the header: [activation tiles | weight buffer], aliased by attention
+  int64_t wbuf_offset;         // weight buffer offset inside the scratch region
   int do_sample_phase;     // 1: logits -> token inside the kernel (ptts_decode_steps); 0: stop at the logits
   int sample_items;        // ceil(V / 32)
   int* progress;           // debug: last phase each CTA arrived at (printed on a barrier timeout)
