@@ -254,7 +254,7 @@ static bool setup_fused(ptts_session* s) {
   if (p.nt_fc1 > ntmax) ntmax = p.nt_fc1;
   if (p.nt_heads > ntmax) ntmax = p.nt_heads;
   const int64_t tile = (int64_t)32 * (L.H + 8) * 2;
-  const int64_t red = (int64_t)8 * 32 * 8 * ntmax * 4;
+  const int64_t red = (int64_t)8 * 32 * (8 * ntmax + 8) * 4;  // K-reduction scratch [8 warps][32][RS], step.cu
   // weight buffer: the largest per-task slice (nt n-tiles x K, 16 bytes per (n-tile, k-pair) fragment row)
   int64_t wbytes = (int64_t)p.nt_qkv * L.H * 16;
   if ((int64_t)p.nt_h * L.F * 16 > wbytes) wbytes = (int64_t)p.nt_h * L.F * 16;

@@ -129,6 +129,7 @@ struct Smem {
   long long* prof;  // CTA 0 / thread 0 timestamps of the current phase (nullptr = off)
   int pitch;
   int nbuf;
+  int dbg;
 };
 
 __device__ __forceinline__ bf16* tile_of(const Smem& sm, int buf) { return sm.tile0 + (size_t)buf * 32 * sm.pitch; }
@@ -140,7 +141,7 @@ __device__ __forceinline__ bf16* tile_of(const Smem& sm, int buf) { return sm.ti
 __device__ __forceinline__ void stage_tile(Smem& sm, int buf, const bf16* img, int M, bool mark) {
   __syncthreads();  // every generic-proxy access to the buffer (ldmatrix, reduction scratch) is done
   if (threadIdx.x == 0) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // tile buffer: generic accesses (above barrier) before the async write
+    if (!(sm.dbg & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // tile buffer: generic accesses (above barrier) before the async write
     const uint32_t bytes = (uint32_t)(M * sm.pitch * 2);
     mbar_expect_tx(&sm.bars[buf], bytes);
     bulk_g2s(tile_of(sm, buf), img, bytes, &sm.bars[buf]);
@@ -246,39 +247,50 @@ __device__ __forceinline__ void issue_weights(const StepParams& p, Smem& sm, int
   gemm_matrix(p, ph, W, N, K, nt);
   if (task >= N / (8 * nt)) return;
   const uint32_t bytes = (uint32_t)nt * (uint32_t)K * 16u;
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (!(p.dbg & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   mbar_expect_tx(&sm.bars[WBAR], bytes);
   bulk_g2s(const_cast<uint4*>(sm.wbuf), W + (size_t)task * bytes, bytes, &sm.bars[WBAR]);
 }
 __device__ __forceinline__ bool is_attn_phase(const StepParams& p, int ph) { return ph < 8 * p.L && ((ph & 7) == 1 || (ph & 7) == 4); }
 
 // All tasks (n-blocks of 8*NT features) of one linear layer assigned to this CTA.  M = B <= 32 rows.
+// (A single run-time-nt body was tried to shrink the instruction footprint: the predicated inner loop cost more than
+// the smaller code saved -- 1.39 vs 1.32 ms/step.)
 template <int NT>
 __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const GemmDesc& d) {
+  constexpr int NT_MAX = NT, nt = NT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = p.B, H = p.H;
   const int Kc = d.K < H ? d.K : H;
   const int n_chunks = d.K / Kc;
   const int kt_per_chunk = Kc >> 5, KT = d.K >> 5;
-  const int ntasks = d.N / (8 * NT);
   constexpr int FB = 8 * NT;
+  constexpr int RS = (FB & 15) ? FB : FB + 8;  // row stride of the reduction scratch (floats): conflict-free for the epilogue reads
+  const int ntasks = d.N / FB;
   // single-chunk GEMMs with two tile buffers keep the staged tile (and its row statistics) resident across this CTA's
   // tasks: the K-reduction scratch then lives in the second buffer (lm heads: 2-3 tasks per CTA)
   const bool resident = (n_chunks == 1 && sm.nbuf > 1);
+  const int er = threadIdx.x >> 3, ec = threadIdx.x & 7;  // epilogue: this thread owns row er, feature ec of every n-tile
   for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
     const bool fresh = !resident || task == (int)blockIdx.x;
-    const int nt0 = task * NT;
+    const int n0 = task * FB;
     // activations: chunk 0 and, when double-buffered, chunk 1 (the weights were requested a phase ago)
     if (fresh) stage_tile(sm, 0, d.X, M, true);
     if (sm.nbuf > 1 && n_chunks > 1) stage_tile(sm, 1, d.X + d.x_chunk_stride, M, false);
-    if (d.c1 != nullptr && threadIdx.x < 2 * FB)  // this task's c1 | c2 -> shared memory (read in the epilogue, two barriers later)
-      sm.cvec[(threadIdx.x < FB ? 0 : 32) + (threadIdx.x % FB)] = (threadIdx.x < FB ? d.c1 : d.c2)[nt0 * 8 + threadIdx.x % FB];
+    auto y_offset = [&](int n) -> size_t {
+      const int yc = n / d.y_chunk;
+      return (size_t)yc * d.y_chunk_stride + (size_t)er * d.ldy + (n - yc * d.y_chunk);
+    };
+    float rv0 = 0.f;  // residual of this thread's first output: requested now, consumed in the epilogue
+    if (d.epi == EPI_RESIDUAL && er < M) rv0 = DT<bf16>::to_f(d.R[y_offset(n0 + ec)]);
+    if (d.c1 != nullptr && (int)threadIdx.x < 2 * FB)  // this task's c1 | c2 -> shared memory (read in the epilogue, two barriers later)
+      sm.cvec[(threadIdx.x < FB ? 0 : 32) + (threadIdx.x % FB)] = (threadIdx.x < FB ? d.c1 : d.c2)[n0 + threadIdx.x % FB];
     if (task == (int)blockIdx.x) issue_prefetch(p, d.pf);  // next layer's weights / this layer's K/V -> L2, off the critical path
-    float acc[2][NT][4];
+    float acc[2][NT_MAX][4];
 #pragma unroll
     for (int a = 0; a < 2; a++)
 #pragma unroll
-      for (int j = 0; j < NT; j++)
+      for (int j = 0; j < NT_MAX; j++)
 #pragma unroll
         for (int e = 0; e < 4; e++) acc[a][j][e] = 0.f;
 
@@ -302,67 +314,68 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
       const bf16* xs = tile_of(sm, buf);
       for (int kt = warp; kt < kt_per_chunk; kt += ST_WARPS) {  // K split over the 8 warps
         const uint4* wk = sm.wbuf + ((size_t)(c * kt_per_chunk + kt)) * 32 + lane;
-        uint4 w[NT];
+        uint4 w[NT_MAX];
 #pragma unroll
-        for (int j = 0; j < NT; j++) w[j] = wk[(size_t)j * KT * 32];
+        for (int j = 0; j < NT_MAX; j++)
+          if (j < nt) w[j] = wk[(size_t)j * KT * 32];
         uint32_t a[2][2][4];
 #pragma unroll
         for (int mt = 0; mt < 2; mt++)
 #pragma unroll
           for (int j = 0; j < 2; j++) ldmatrix_x4s(a[mt][j], xs + (size_t)(mt * 16 + lrow) * sm.pitch + kt * 32 + j * 16 + lcol);
 #pragma unroll
-        for (int j = 0; j < NT; j++) {
+        for (int j = 0; j < NT_MAX; j++) {
+          if (j < nt) {
 #pragma unroll
-          for (int mt = 0; mt < 2; mt++) {
-            mma_bf16s(acc[mt][j], a[mt][0], w[j].x, w[j].y);
-            mma_bf16s(acc[mt][j], a[mt][1], w[j].z, w[j].w);
+            for (int mt = 0; mt < 2; mt++) {
+              mma_bf16s(acc[mt][j], a[mt][0], w[j].x, w[j].y);
+              mma_bf16s(acc[mt][j], a[mt][1], w[j].z, w[j].w);
+            }
           }
         }
       }
       if (sm.nbuf > 1 && c + 2 < n_chunks) stage_tile(sm, buf, d.X + (c + 2) * d.x_chunk_stride, M, false);
     }
     prof_mark(sm.prof, 3);
-    const int n0 = nt0 * 8;
-    auto y_offset = [&](int r, int n) -> size_t {
-      const int yc = n / d.y_chunk;
-      return (size_t)yc * d.y_chunk_stride + (size_t)r * d.ldy + (n - yc * d.y_chunk);
-    };
-    float rv0 = 0.f;  // residual of this thread's first output, requested now: its L2 latency overlaps the K reduction
-    if (d.epi == EPI_RESIDUAL && (int)threadIdx.x / FB < M) rv0 = DT<bf16>::to_f(d.R[y_offset(threadIdx.x / FB, n0 + threadIdx.x % FB)]);
     __syncthreads();
     // the weight buffer is free: request the next job's slice (next task of this matrix, else the next phase's matrix;
     // when an attention phase comes next its end issues the copy -- the buffer may alias attention scratch)
     if (task + (int)gridDim.x < ntasks) issue_weights(p, sm, d.ph, task + gridDim.x);
     else if (d.ph < 8 * p.L && !is_attn_phase(p, d.ph + 1)) issue_weights(p, sm, d.ph + 1, blockIdx.x);
     if (fresh && d.c1 != nullptr) row_stat_finalize(sm.part, d.K, M, p.eps, sm.stats);  // (mean, rstd) per row; read in the epilogue
-    float* red = reinterpret_cast<float*>(resident ? tile_of(sm, 1) : tile_of(sm, 0));  // [8][32][FB], in an idle tile buffer
+    float* red = reinterpret_cast<float*>(resident ? tile_of(sm, 1) : tile_of(sm, 0));  // [8][32][RS], in an idle tile buffer
     {
       const int g = lane >> 2, t = lane & 3;
 #pragma unroll
       for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-        for (int j = 0; j < NT; j++) {
-          float* base = red + ((size_t)warp * 32 + mt * 16 + g) * FB + j * 8 + 2 * t;
-          base[0] = acc[mt][j][0];
-          base[1] = acc[mt][j][1];
-          base[8 * FB] = acc[mt][j][2];
-          base[8 * FB + 1] = acc[mt][j][3];
+        for (int j = 0; j < NT_MAX; j++) {
+          if (j < nt) {
+            float* base = red + ((size_t)warp * 32 + mt * 16 + g) * RS + j * 8 + 2 * t;
+            *reinterpret_cast<float2*>(base) = make_float2(acc[mt][j][0], acc[mt][j][1]);
+            *reinterpret_cast<float2*>(base + 8 * RS) = make_float2(acc[mt][j][2], acc[mt][j][3]);
+          }
         }
     }
     __syncthreads();
-    for (int o = threadIdx.x; o < 32 * FB; o += ST_THREADS) {
-      const int r = o / FB, cidx = o - r * FB;
-      if (r >= M) continue;
-      float v = 0.f;
+    if (er < M) {
+      const float mean = sm.stats[2 * er], rstd = sm.stats[2 * er + 1];
 #pragma unroll
-      for (int w = 0; w < ST_WARPS; w++) v += red[((size_t)w * 32 + r) * FB + cidx];
-      if (d.c1 != nullptr) v = sm.stats[2 * r + 1] * (v - sm.stats[2 * r] * sm.cvec[cidx]) + sm.cvec[32 + cidx];
-      v = DT<bf16>::rnd(v);
-      if (d.epi == EPI_ACT) v = apply_act(v, p.act);
-      const size_t yo = y_offset(r, n0 + cidx);
-      if (d.epi == EPI_RESIDUAL) v = (o == (int)threadIdx.x ? rv0 : DT<bf16>::to_f(d.R[yo])) + v;
-      if (d.epi == EPI_F32) reinterpret_cast<float*>(d.Y)[yo] = v;
-      else reinterpret_cast<bf16*>(d.Y)[yo] = __float2bfloat16_rn(v);
+      for (int j = 0; j < NT_MAX; j++) {
+        if (j < nt) {
+          const int cidx = j * 8 + ec;
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < ST_WARPS; w++) v += red[((size_t)w * 32 + er) * RS + cidx];
+          if (d.c1 != nullptr) v = rstd * (v - mean * sm.cvec[cidx]) + sm.cvec[32 + cidx];
+          v = DT<bf16>::rnd(v);
+          if (d.epi == EPI_ACT) v = apply_act(v, p.act);
+          const size_t yo = y_offset(n0 + cidx);
+          if (d.epi == EPI_RESIDUAL) v = (j == 0 ? rv0 : DT<bf16>::to_f(d.R[yo])) + v;
+          if (d.epi == EPI_F32) reinterpret_cast<float*>(d.Y)[yo] = v;
+          else reinterpret_cast<bf16*>(d.Y)[yo] = __float2bfloat16_rn(v);
+        }
+      }
     }
     prof_mark(sm.prof, 4);
   }
@@ -421,6 +434,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
   sm.wbuf = reinterpret_cast<const uint4*>(smem_raw + ST_HEADER + p.wbuf_offset);
   sm.pitch = H + 8;
   sm.nbuf = p.nbuf;
+  sm.dbg = p.dbg;
   sm.tile0 = reinterpret_cast<bf16*>(sm.scratch);
   sm.parity = 0;
   sm.prof = nullptr;
