@@ -261,6 +261,10 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
   if (n_chunks > 0) issue(0);
   if (n_chunks > 1) issue(1);
 
+  // the first query head's elements are requested before the K/V append below (its stores would otherwise order the loads
+  // behind a second L2 round trip)
+  const T* q_first = reinterpret_cast<const T*>(p.q) + (size_t)b * p.ldq + p.q_col0 + (size_t)(kvh * rep) * HD;
+  const float qf0 = DT<T>::to_f(q_first[lo]), qf1 = DT<T>::to_f(q_first[hi]);
   if (!p.cross && part == 0) {  // this step's K (rotary applied) and V: to the cache (for later steps) and to shared memory (for now)
     const T* ksrc = reinterpret_cast<const T*>(p.knew) + (size_t)b * p.ldkv + p.k_col0 + kvh * HD;
     const T* vsrc = reinterpret_cast<const T*>(p.vnew) + (size_t)b * p.ldkv + p.v_col0 + kvh * HD;
@@ -285,7 +289,7 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
     const int h = kvh * rep + rr;
     {
       const T* qsrc = reinterpret_cast<const T*>(p.q) + (size_t)b * p.ldq + p.q_col0 + h * HD;
-      float x0 = DT<T>::to_f(qsrc[lo]), x1 = DT<T>::to_f(qsrc[hi]);
+      float x0 = (rr == 0) ? qf0 : DT<T>::to_f(qsrc[lo]), x1 = (rr == 0) ? qf1 : DT<T>::to_f(qsrc[hi]);
       if (p.rope) {
         const float y0 = rope_elem<T>(x0, x1, lo, rope_cos, rope_sin);
         const float y1 = rope_elem<T>(x1, x0, hi, rope_cos, rope_sin);

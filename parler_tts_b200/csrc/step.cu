@@ -281,10 +281,10 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
       const int yc = n / d.y_chunk;
       return (size_t)yc * d.y_chunk_stride + (size_t)er * d.ldy + (n - yc * d.y_chunk);
     };
-    float rv0 = 0.f;  // residual of this thread's first output: requested now, consumed in the epilogue
-    if (d.epi == EPI_RESIDUAL && er < M) rv0 = DT<bf16>::to_f(d.R[y_offset(n0 + ec)]);
-    if (d.c1 != nullptr && (int)threadIdx.x < 2 * FB)  // this task's c1 | c2 -> shared memory (read in the epilogue, two barriers later)
-      sm.cvec[(threadIdx.x < FB ? 0 : 32) + (threadIdx.x % FB)] = (threadIdx.x < FB ? d.c1 : d.c2)[n0 + threadIdx.x % FB];
+    unsigned short rraw = 0;  // residual of this thread's first output (raw bf16 bits: no dependent instruction until the epilogue)
+    if (d.epi == EPI_RESIDUAL && er < M) rraw = *reinterpret_cast<const unsigned short*>(d.R + y_offset(n0 + ec));
+    float cv = 0.f;  // this task's c1 | c2 (one element per thread): requested now, parked in shared memory after the MMA loop
+    if (d.c1 != nullptr && (int)threadIdx.x < 2 * FB) cv = (threadIdx.x < FB ? d.c1 : d.c2)[n0 + threadIdx.x % FB];
     if (task == (int)blockIdx.x) issue_prefetch(p, d.pf);  // next layer's weights / this layer's K/V -> L2, off the critical path
     float acc[2][NT_MAX][4];
 #pragma unroll
@@ -337,6 +337,7 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
       if (sm.nbuf > 1 && c + 2 < n_chunks) stage_tile(sm, buf, d.X + (c + 2) * d.x_chunk_stride, M, false);
     }
     prof_mark(sm.prof, 3);
+    if (d.c1 != nullptr && (int)threadIdx.x < 2 * FB) sm.cvec[(threadIdx.x < FB ? 0 : 32) + (threadIdx.x % FB)] = cv;  // read two barriers later
     __syncthreads();
     // the weight buffer is free: request the next job's slice (next task of this matrix, else the next phase's matrix;
     // when an attention phase comes next its end issues the copy -- the buffer may alias attention scratch)
@@ -371,7 +372,7 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
           v = DT<bf16>::rnd(v);
           if (d.epi == EPI_ACT) v = apply_act(v, p.act);
           const size_t yo = y_offset(n0 + cidx);
-          if (d.epi == EPI_RESIDUAL) v = (j == 0 ? rv0 : DT<bf16>::to_f(d.R[yo])) + v;
+          if (d.epi == EPI_RESIDUAL) v = (j == 0 ? __bfloat162float(__ushort_as_bfloat16(rraw)) : DT<bf16>::to_f(d.R[yo])) + v;
           if (d.epi == EPI_F32) reinterpret_cast<float*>(d.Y)[yo] = v;
           else reinterpret_cast<bf16*>(d.Y)[yo] = __float2bfloat16_rn(v);
         }
