@@ -187,6 +187,10 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# DRAM bytes of one fused decode-step launch from the committed ncu --set full capture (profiles/r01_step_ncu_full.md)
+NCU_STEP_DRAM_BYTES = 1171574000 + 10182656
+
+
 def cpu_baseline_quick():
     """~10-30 s of CPU work: the oracle port on a bounded sample of the same workload (rank 0, N=1)."""
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
@@ -195,7 +199,7 @@ def cpu_baseline_quick():
     from oracle.decoder import OracleDecoder
     from oracle.sampling import generate_tokens
     cfg = mini_cfg()
-    Bc, n_dec = 32, 8
+    Bc, n_dec = 32, 32   # ~0.36 s per decode step on 64 threads -> ~12 s
     dec = OracleDecoder(cfg, make_decoder_weights(cfg, seed=0), torch.float32)
     enc, enc_mask, prompt, pmask = synthetic_inputs(Bc, cfg.hidden_size, 1)
     gen = dict(max_length=n_dec + 1, do_sample=True, top_k=50, min_new_tokens=n_dec)
@@ -356,7 +360,9 @@ def main():
                            "token matrix read back to host"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "decode_step_kernel (one persistent cooperative kernel per token: embed + 24 x 8 phases + heads + sample)",
+                         "traffic": NCU_STEP_DRAM_BYTES, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one decode_step_kernel launch "
+                         "(T=73 cached keys; algorithmic 1.16e9 there), ncu --set full capture summarised in profiles/r01_step_ncu_full.md",
+                         "peak_source": peak_src, "kernel": "decode_step_kernel (one persistent cooperative kernel per token: embed + 24 x 8 phases + heads + sample)",
                          "ms_per_decode_step": dec_ms / n_timed, "algorithmic_bytes_per_step_avg": byts / n_timed},
         }
         if dac_info is not None:
