@@ -89,7 +89,11 @@ __device__ __forceinline__ uint4 ldg_stream_s(const uint4* p) {
 // ---- device-wide barrier ------------------------------------------------------------------------
 // Arrive = red.release (cumulative over the CTA's writes ordered by the preceding bar.sync); the spin is a
 // RELAXED load (an acquire load would invalidate L1 on every poll); one acquire fence after the exit.
-__device__ __forceinline__ unsigned grid_sync(unsigned* ctr, unsigned target, int* progress = nullptr, int ph = 0) {
+// `side` runs on thread 32 between the two CTA barriers, i.e. while thread 0 polls: work that needs the whole CTA to be
+// past its shared-memory accesses but not the other CTAs (the next phase's weight copy) costs nothing there.
+struct NoSideJob { __device__ __forceinline__ void operator()() const {} };
+template <typename Side = NoSideJob>
+__device__ __forceinline__ unsigned grid_sync(unsigned* ctr, unsigned target, int* progress = nullptr, int ph = 0, Side side = Side()) {
   target += gridDim.x;
   // this thread's global writes (generic proxy) -> later TMA reads by other CTAs (async proxy): the proxy fence sits on the
   // writer side of the release/acquire chain, where it overlaps the store drain instead of delaying the next tile copy
@@ -107,6 +111,8 @@ __device__ __forceinline__ unsigned grid_sync(unsigned* ctr, unsigned target, in
       }
     }
     fence_acq_rel_gpu();
+  } else if (threadIdx.x == 32) {
+    side();
   }
   __syncthreads();
   return target;
@@ -241,8 +247,7 @@ __device__ __forceinline__ void gemm_matrix(const StepParams& p, int ph, const c
 }
 
 // Called by all threads AFTER a __syncthreads() that retired every reader of the weight buffer.
-__device__ __forceinline__ void issue_weights(const StepParams& p, Smem& sm, int ph, int task) {
-  if (threadIdx.x != 0) return;
+__device__ __forceinline__ void issue_weights_thread(const StepParams& p, Smem& sm, int ph, int task) {  // ONE thread
   const char* W; int N, K, nt;
   gemm_matrix(p, ph, W, N, K, nt);
   if (task >= N / (8 * nt)) return;
@@ -250,6 +255,9 @@ __device__ __forceinline__ void issue_weights(const StepParams& p, Smem& sm, int
   if (!(p.dbg & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   mbar_expect_tx(&sm.bars[WBAR], bytes);
   bulk_g2s(const_cast<uint4*>(sm.wbuf), W + (size_t)task * bytes, bytes, &sm.bars[WBAR]);
+}
+__device__ __forceinline__ void issue_weights(const StepParams& p, Smem& sm, int ph, int task) {
+  if (threadIdx.x == 0) issue_weights_thread(p, sm, ph, task);
 }
 __device__ __forceinline__ bool is_attn_phase(const StepParams& p, int ph) { return ph < 8 * p.L && ((ph & 7) == 1 || (ph & 7) == 4); }
 
@@ -339,10 +347,9 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
     prof_mark(sm.prof, 3);
     if (d.c1 != nullptr && (int)threadIdx.x < 2 * FB) sm.cvec[(threadIdx.x < FB ? 0 : 32) + (threadIdx.x % FB)] = cv;  // read two barriers later
     __syncthreads();
-    // the weight buffer is free: request the next job's slice (next task of this matrix, else the next phase's matrix;
-    // when an attention phase comes next its end issues the copy -- the buffer may alias attention scratch)
+    // the weight buffer is free: request the next task's slice of this matrix (the NEXT phase's first slice is requested
+    // from inside the device-wide barrier, see the phase loop)
     if (task + (int)gridDim.x < ntasks) issue_weights(p, sm, d.ph, task + gridDim.x);
-    else if (d.ph < 8 * p.L && !is_attn_phase(p, d.ph + 1)) issue_weights(p, sm, d.ph + 1, blockIdx.x);
     if (fresh && d.c1 != nullptr) row_stat_finalize(sm.part, d.K, M, p.eps, sm.stats);  // (mean, rstd) per row; read in the epilogue
     float* red = reinterpret_cast<float*>(resident ? tile_of(sm, 1) : tile_of(sm, 0));  // [8][32][RS], in an idle tile buffer
     {
@@ -380,8 +387,6 @@ __device__ __forceinline__ void gemm_tasks(const StepParams& p, Smem& sm, const 
     }
     prof_mark(sm.prof, 4);
   }
-  // a CTA without a task in this matrix still has to request its slice of the next one
-  if ((int)blockIdx.x >= ntasks && d.ph < 8 * p.L && !is_attn_phase(p, d.ph + 1)) issue_weights(p, sm, d.ph + 1, blockIdx.x);
 }
 
 __device__ __forceinline__ void run_gemm(const StepParams& p, Smem& sm, const GemmDesc& d, int nt) {
@@ -405,8 +410,6 @@ __device__ __forceinline__ void attn_phase(const StepParams& p, Smem& sm, const 
   __syncthreads();  // the tile / reduction scratch of the previous GEMM phase is dead
   for (int it = blockIdx.x + gridDim.x * pair; it < items; it += gridDim.x * (ST_WARPS / 2))
     attention_decode_item_warp<bf16>(a, it / nkv, it % nkv, pos, region, bars, lane, att_parity, part, 2, xch, pair + 1);
-  __syncthreads();  // attention scratch is dead: the next GEMM's weight slice may land (it overlaps the device-wide barrier)
-  issue_weights(p, sm, ph + 1, blockIdx.x);
 }
 
 template <int ITEMS>
@@ -419,6 +422,7 @@ template <int ITEMS>
 __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Ctrl* ctrl = p.sa.ctrl;
+  if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(size_t)(8 * p.L + 2) * 8 + 3] = clock64();  // kernel entry
   if (ctrl->active == 0) return;  // generation finished: the rest of the enqueued steps are no-ops
   const int cur_len = ctrl->cur_len;
   const unsigned gen = (unsigned)ctrl->launch_gen;
@@ -456,7 +460,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
   issue_weights(p, sm, 0, blockIdx.x);  // layer 0's qkv slice lands during the embedding phase
 
   const char* blob = p.blob;
-  sm.prof = (p.prof != nullptr && blockIdx.x == 0) ? p.prof : nullptr;
+  // (Several tokens per launch were tried -- loop here, one extra barrier per token: no gain, back-to-back cooperative
+  // launches leave no measurable gap on the device.)
+  long long* const prof0 = (p.prof != nullptr && blockIdx.x == 0) ? p.prof : nullptr;
+  sm.prof = prof0;
   prof_mark(sm.prof, 0);
   // ---- phase 0: embeddings + L2 prefetch of layer 0 ----
   if (tid == 0) {
@@ -496,7 +503,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
 #pragma unroll 1
   for (int ph = 0; ph <= 8 * p.L; ph++) {
     const int l = ph >> 3, sub = (ph == 8 * p.L) ? 8 : (ph & 7);
-    sm.prof = (p.prof != nullptr && blockIdx.x == 0) ? p.prof + (size_t)(ph + 1) * 8 : nullptr;
+    sm.prof = prof0 ? prof0 + (size_t)(ph + 1) * 8 : nullptr;
     prof_mark(sm.prof, 0);
     const char* lb = blob + p.layer0 + p.layer_stride * (l < p.L ? l : p.L - 1);
     if (sub == 1 || sub == 4) {
@@ -586,15 +593,24 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_step_kernel(const __grid
       run_gemm(p, sm, g, nt);
     }
     prof_mark(sm.prof, 6);
-    if (ph < 8 * p.L) bar_target = grid_sync(bar_ctr, bar_target, p.progress, ph + 1);
+    if (ph < 8 * p.L) {
+      // while thread 0 polls the barrier, thread 32 requests this CTA's weight slice of the next phase when that is a GEMM
+      // (every reader of the weight buffer -- and of the attention scratch it may alias -- is past the CTA barrier by then)
+      const int wph = is_attn_phase(p, ph + 1) ? -1 : ph + 1;
+      bar_target = grid_sync(bar_ctr, bar_target, p.progress, ph + 1, [&]() { if (wph >= 0) issue_weights_thread(p, sm, wph, blockIdx.x); });
+    }
     prof_mark(sm.prof, 7);
   }
   bar_target = grid_sync(bar_ctr, bar_target);
+  sm.prof = prof0 ? prof0 + (size_t)(8 * p.L + 2) * 8 : nullptr;  // tail row: barrier / sampling / barrier
+  prof_mark(sm.prof, 0);
   if (p.do_sample_phase) {
     const ptts_gen_params gp = *p.sa.gen;
     const int BK = p.B * p.K;
     sample_phase<ITEMS>(p.sa, gp, BK, cur_len);
+    prof_mark(sm.prof, 1);
     bar_target = grid_sync(bar_ctr, bar_target);
+    prof_mark(sm.prof, 2);
   }
   if (blockIdx.x == 0 && tid == 0) {
     if (p.do_sample_phase) {

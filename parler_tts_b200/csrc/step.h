@@ -33,7 +33,7 @@ struct StepParams {
   int sample_items;        // ceil(V / 32)
   int* progress;           // debug: last phase each CTA arrived at (printed on a barrier timeout)
   int dbg;                 // PTTS_DBG experiment bits (1: no weight L2 prefetch, 2: no K/V prefetch)
-  long long* prof;         // optional [(8L+2)][8] clock64 timestamps written by CTA 0 (debug / profiles)
+  long long* prof;         // optional [(8L+3)][8] clock64 timestamps written by CTA 0 (debug / profiles)
 };
 
 int step_smem_bytes(const StepParams& p);

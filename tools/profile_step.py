@@ -24,7 +24,7 @@ sess.prefill(pr, pm, enc, em)
 sess.sample()
 sess.decode_steps(steps_before)
 nph = 8 * 24 + 2
-buf = torch.zeros(nph * 8, dtype=torch.int64, device=dev)
+buf = torch.zeros((nph + 1) * 8, dtype=torch.int64, device=dev)
 _lib.check(_lib.lib().ptts_session_set_profile(sess.h, _lib.ptr(buf)))
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -32,7 +32,7 @@ e0.record()
 sess.decode_steps(1)
 e1.record()
 torch.cuda.synchronize()
-t = buf.cpu().view(nph, 8).numpy()
+t = buf.cpu().view(nph + 1, 8).numpy()
 _lib.check(_lib.lib().ptts_session_set_profile(sess.h, None))
 ghz = 1.965
 names = {0: "ln+qkv", 1: "self-attn", 2: "o-proj", 3: "ln+q_cross", 4: "cross-attn", 5: "o_cross", 6: "ln+fc1", 7: "fc2"}
@@ -58,5 +58,7 @@ r = t[0]
 print(f"embed work {(r[6]-r[0])/ghz/1e3:.2f} barrier {(r[7]-r[6])/ghz/1e3:.2f}")
 r = t[8 * 24 + 1]
 print(f"heads work {(r[6]-r[0])/ghz/1e3:.2f} | tile {(r[1]-r[0])/ghz/1e3:.2f} ln {(r[2]-r[1])/ghz/1e3:.2f} mma {(r[3]-r[2])/ghz/1e3:.2f} epi {(r[4]-r[3])/ghz/1e3:.2f}")
+r = t[nph]
+print(f"prologue (entry -> embed start) {(t[0,0]-r[3])/ghz/1e3:.2f} | post-heads barrier {(r[0]-t[nph-1,6])/ghz/1e3:.2f} | sampling {(r[1]-r[0])/ghz/1e3:.2f} | last barrier {(r[2]-r[1])/ghz/1e3:.2f} | kernel span {(r[2]-r[3])/ghz/1e3:.1f} us")
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump({"step_us": e0.elapsed_time(e1) * 1e3, "phases_us": out, "T": bench.P_LEN + steps_before + 2}, open("gpurun_out/step_phases.json", "w"), indent=1)
