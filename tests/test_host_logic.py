@@ -131,3 +131,22 @@ def test_generation_config_update_splits_model_kwargs():
     gc = GenerationConfig()
     rest = gc.update(do_sample=False, max_new_tokens=12, prompt_input_ids="x")
     assert gc.do_sample is False and gc.max_new_tokens == 12 and rest == {"prompt_input_ids": "x"}
+
+
+def test_layernorm_fold_algebra():
+    """The identity ptts_decoder_finalize (gemm.cu fold_layernorm_kernel) and ln_stats.cuh rely on, in float64 numpy:
+    LN(x) W^T == rstd * (x W'^T - mean * c1) + c2 with W' = gamma*W, c1 = rowsum(W'), c2 = W beta, and the row statistics
+    taken as mean = S1/K, var = S2/K - mean^2 from S1 = x.1 and S2 = diag(x x^T) (what the tensor-core pass accumulates)."""
+    rng = np.random.default_rng(3)
+    K, N, M, eps = 64, 24, 5, 1e-5
+    x = rng.normal(size=(M, K)) * 2.0 + rng.normal(size=(M, 1)) * 3.0   # rows with a non-zero mean
+    gamma, beta, W = rng.normal(size=K) + 1.0, rng.normal(size=K), rng.normal(size=(N, K))
+    mu, var = x.mean(1, keepdims=True), x.var(1, keepdims=True)
+    ref = (((x - mu) / np.sqrt(var + eps)) * gamma + beta) @ W.T
+    Wp, c2 = W * gamma, W @ beta
+    c1 = Wp.sum(1)
+    S1, S2 = x @ np.ones(K), np.diag(x @ x.T)
+    mean = S1 / K
+    rstd = 1.0 / np.sqrt(np.maximum(S2 / K - mean * mean, 0.0) + eps)
+    got = rstd[:, None] * (x @ Wp.T - mean[:, None] * c1) + c2
+    np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9)
