@@ -4,7 +4,8 @@
   MinNewTokensLength / Temperature / TopK / TopP warpers
                                       transformers 4.46.1 `generation/logits_process.py` (not vendored in
                                       /root/reference; same arithmetic in the container's 5.5.0 at
-                                      logits_process.py:225-233, 297-299, 521-533, 581-586)
+                                      logits_process.py:225-233, 297-299, 521-533, 581-586); PINNED bit-exact
+                                      against those classes by tests/golden/warpers.npz (make_golden.gen_warpers)
   `_sample` loop                      transformers 4.46.1 `generation/utils.py::_sample` (restated; the
                                       reference calls it at modeling_parler_tts.py:3564)
   processor order                     [MinNewTokens, ParlerTTS (custom), Temperature, TopK, TopP]

@@ -182,8 +182,43 @@ def gen_dac():
     np.savez_compressed(os.path.join(HERE, "dac_decode.npz"), codes=codes.numpy(), z=z.numpy(), audio=audio.numpy())
 
 
+def gen_warpers():
+    """The warper / processor classes GenerationMixin._sample applies around the Parler processor, executed from the installed
+    transformers (5.5.0: same arithmetic as the 4.46.1 the reference pins, logits_process.py:225-233, 297-299, 521-533,
+    581-586).  Pins oracle.sampling.{min_new_tokens, temperature, top_k, top_p}."""
+    from transformers.generation.logits_process import (MinNewTokensLengthLogitsProcessor, TemperatureLogitsWarper,
+                                                        TopKLogitsWarper, TopPLogitsWarper)
+    g = torch.Generator().manual_seed(7)
+    R, V, eos = 6, 96, 64
+    out = {"meta": np.array([R, V, eos])}
+    scores = torch.randn(R, V, generator=g) * 3.0
+    scores[1, 10:14] = scores[1, 9]          # ties around the k-th value
+    scores[2] = scores[2].round()            # many duplicates
+    scores[3, :50] = -float("inf")           # already-masked entries (what the Parler processor leaves behind)
+    out["scores"] = scores.numpy()
+    ids = torch.zeros(R, 5, dtype=torch.long)
+    for n, (cur, mn) in enumerate([(1, 3), (3, 3), (4, 3), (2, 10)]):   # cur_len - prompt_len(1) < min_new -> EOS masked
+        proc = MinNewTokensLengthLogitsProcessor(prompt_length_to_skip=1, min_new_tokens=mn, eos_token_id=eos)
+        out[f"minnew{n}_args"] = np.array([cur, mn])
+        out[f"minnew{n}"] = proc(ids[:, :cur], scores.clone()).numpy()
+    for n, t in enumerate([0.7, 1.3]):
+        out[f"temp{n}_arg"] = np.array([t], dtype=np.float64)
+        out[f"temp{n}"] = TemperatureLogitsWarper(t)(ids, scores.clone()).numpy()
+    for n, k in enumerate([1, 5, 50, 200]):
+        out[f"topk{n}_arg"] = np.array([k])
+        out[f"topk{n}"] = TopKLogitsWarper(top_k=k)(ids, scores.clone()).numpy()
+    for n, pp in enumerate([0.1, 0.5, 0.9, 0.999]):
+        out[f"topp{n}_arg"] = np.array([pp], dtype=np.float64)
+        out[f"topp{n}"] = TopPLogitsWarper(top_p=pp)(ids, scores.clone()).numpy()
+    # the chain as _sample applies it: temperature -> top-k -> top-p
+    chain = TopPLogitsWarper(top_p=0.8)(ids, TopKLogitsWarper(top_k=20)(ids, TemperatureLogitsWarper(0.9)(ids, scores.clone())))
+    out["chain"] = chain.numpy()
+    np.savez_compressed(os.path.join(HERE, "warpers.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    gen_warpers()
     pt = import_reference()
     gen_delay(pt)
     gen_logits_processor(pt)

@@ -122,3 +122,26 @@ def test_generate_loop_smoke():
     assert raw.shape[0] == B * cfg.num_codebooks and raw.shape[1] <= 14
     fr = frames_from_raw(raw, out["delay_mask"], cfg, B)
     assert fr.shape == (B, cfg.num_codebooks, raw.shape[1] - cfg.num_codebooks)
+
+
+def test_warpers_against_transformers_classes(golden_dir):
+    """oracle.sampling's restatement of the HF processors / warpers around the Parler processor, bit-exact against the
+    outputs of the installed transformers classes (fixture: make_golden.gen_warpers)."""
+    from oracle.sampling import min_new_tokens, temperature, top_k, top_p
+    z = np.load(os.path.join(golden_dir, "warpers.npz"))
+    R, V, eos = (int(v) for v in z["meta"])
+    scores = z["scores"]
+    n = 0
+    while f"minnew{n}" in z:
+        cur, mn = (int(v) for v in z[f"minnew{n}_args"])
+        assert np.array_equal(min_new_tokens(scores.copy(), cur, 1, mn, eos), z[f"minnew{n}"]), ("min_new", n)
+        n += 1
+    assert n == 4
+    for n in range(2):
+        assert np.array_equal(temperature(scores.copy(), float(z[f"temp{n}_arg"][0])), z[f"temp{n}"]), ("temperature", n)
+    for n in range(4):
+        assert np.array_equal(top_k(scores.copy(), int(z[f"topk{n}_arg"][0])), z[f"topk{n}"]), ("top_k", n)
+    for n in range(4):
+        assert np.array_equal(top_p(scores.copy(), float(z[f"topp{n}_arg"][0])), z[f"topp{n}"]), ("top_p", n)
+    chain = top_p(top_k(temperature(scores.copy(), 0.9), 20), 0.8)
+    assert np.array_equal(chain, z["chain"])
