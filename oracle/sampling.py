@@ -7,7 +7,8 @@
                                       logits_process.py:225-233, 297-299, 521-533, 581-586); PINNED bit-exact
                                       against those classes by tests/golden/warpers.npz (make_golden.gen_warpers)
   `_sample` loop                      transformers 4.46.1 `generation/utils.py::_sample` (restated; the
-                                      reference calls it at modeling_parler_tts.py:3564)
+                                      reference calls it at modeling_parler_tts.py:3564); PINNED bit-exact against the
+                                      installed transformers' `_sample` on scripted logits (tests/golden/sample_loop.npz)
   processor order                     [MinNewTokens, ParlerTTS (custom), Temperature, TopK, TopP]
                                       (`_get_logits_processor`: defaults, then merged custom list, then warpers)
 """

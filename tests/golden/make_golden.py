@@ -216,12 +216,92 @@ def gen_warpers():
     np.savez_compressed(os.path.join(HERE, "warpers.npz"), **out)
 
 
+def gen_sample_loop(pt):
+    """GenerationMixin._sample of the installed transformers (5.5.0; token selection, pad-after-EOS and stopping logic are
+    the same statements as in the 4.46.1 the reference calls at modeling_parler_tts.py:3564) driven by SCRIPTED logits through
+    a stub model, with the processor list in the order `_get_logits_processor` builds it for the reference
+    ([MinNewTokens, ParlerTTSLogitsProcessor (reference class, executed), Temperature, TopK, TopP]) and the stopping criteria
+    [MaxLength, EosToken].  Pins oracle.sampling.generate_tokens' loop glue (greedy and sampled)."""
+    import contextlib
+    from types import SimpleNamespace
+    from transformers import GenerationConfig
+    from transformers.generation.utils import GenerationMixin
+    from transformers.generation.logits_process import (LogitsProcessorList, MinNewTokensLengthLogitsProcessor,
+                                                        TemperatureLogitsWarper, TopKLogitsWarper, TopPLogitsWarper)
+    from transformers.generation.stopping_criteria import StoppingCriteriaList, MaxLengthCriteria, EosTokenCriteria
+    from parler_tts.logits_processors import ParlerTTSLogitsProcessor
+
+    B, K, V, eos, pad, bos = 2, 4, 96, 64, 64, 65
+    L = 16                                     # max_length incl. the BOS column
+    g = torch.Generator().manual_seed(23)
+    script = torch.randn(L, B * K, V, generator=g) * 2.0
+    script[:, :, eos] -= 4.0                   # EOS unlikely unless planted
+    script[:, :, bos] = -30.0
+    # planted EOS preferences: sample 0 finishes early through the cascade, sample 1 runs into max_length
+    for step, row in [(3, 0), (5, 1), (6, 2), (8, 3), (9, 4)]:
+        script[step, row, eos] = 25.0
+
+    class Stub(GenerationMixin):
+        config = SimpleNamespace(is_encoder_decoder=False)
+
+        def __init__(self):
+            self.calls = 0
+
+        def _logits(self):
+            out = SimpleNamespace(logits=script[self.calls][:, None, :].clone())
+            self.calls += 1
+            return out
+
+        def _valid_auto_compile_criteria(self, *a, **k):
+            return False
+
+        def _prefill(self, input_ids, generation_config, model_kwargs, **k):
+            return self._logits()
+
+        def prepare_inputs_for_generation(self, input_ids, **k):
+            return {}
+
+        def __call__(self, **k):
+            return self._logits()
+
+        def _optimize_model_for_decode(self):
+            return contextlib.nullcontext()
+
+        def _update_model_kwargs_for_generation(self, outputs, model_kwargs, **k):
+            return model_kwargs
+
+    out = {"meta": np.array([B, K, V, eos, pad, bos, L]), "script": script.numpy()}
+    cases = [dict(do_sample=False, min_new=0), dict(do_sample=False, min_new=6),
+             dict(do_sample=True, min_new=2, temperature=0.8, top_k=12, top_p=0.9, seed=5)]
+    for n, c in enumerate(cases):
+        procs = [MinNewTokensLengthLogitsProcessor(1, c["min_new"], eos)] if c["min_new"] > 0 else []
+        procs.append(ParlerTTSLogitsProcessor(eos, K, B, "cpu"))
+        if c["do_sample"]:
+            procs += [TemperatureLogitsWarper(c["temperature"]), TopKLogitsWarper(top_k=c["top_k"]), TopPLogitsWarper(top_p=c["top_p"])]
+        gc = GenerationConfig(do_sample=c["do_sample"], pad_token_id=pad, eos_token_id=eos, bos_token_id=bos, max_length=L)
+        gc._pad_token_tensor = torch.tensor(pad)
+        if not hasattr(gc, "is_assistant"):
+            gc.is_assistant = False
+        stub = Stub()
+        ids = torch.full((B * K, 1), bos, dtype=torch.long)
+        if c["do_sample"]:
+            torch.manual_seed(c["seed"])
+        seq = stub._sample(ids, LogitsProcessorList(procs), StoppingCriteriaList([MaxLengthCriteria(L), EosTokenCriteria(eos)]),
+                           gc, synced_gpus=False, streamer=None, use_cache=True)
+        out[f"case{n}_cfg"] = np.array([int(c["do_sample"]), c["min_new"], c.get("top_k", 0), c.get("seed", 0)])
+        out[f"case{n}_fcfg"] = np.array([c.get("temperature", 1.0), c.get("top_p", 1.0)])
+        out[f"case{n}_seq"] = seq.numpy()
+        out[f"case{n}_calls"] = np.array([stub.calls])
+    np.savez_compressed(os.path.join(HERE, "sample_loop.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     gen_warpers()
     pt = import_reference()
     gen_delay(pt)
     gen_logits_processor(pt)
+    gen_sample_loop(pt)
     gen_decoder(pt)
     gen_dac()
     for f in sorted(os.listdir(HERE)):

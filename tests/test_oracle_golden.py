@@ -145,3 +145,41 @@ def test_warpers_against_transformers_classes(golden_dir):
         assert np.array_equal(top_p(scores.copy(), float(z[f"topp{n}_arg"][0])), z[f"topp{n}"]), ("top_p", n)
     chain = top_p(top_k(temperature(scores.copy(), 0.9), 20), 0.8)
     assert np.array_equal(chain, z["chain"])
+
+
+def test_sample_loop_against_transformers_sample(golden_dir):
+    """oracle.sampling.generate_tokens' loop glue (processor order, pad-after-EOS, EOS / max-length stopping, one multinomial per
+    step) against GenerationMixin._sample of the installed transformers run on scripted logits with the reference's own
+    ParlerTTSLogitsProcessor (fixture: make_golden.gen_sample_loop) -- greedy, greedy + min_new_tokens, and sampled."""
+    from types import SimpleNamespace
+    z = np.load(os.path.join(golden_dir, "sample_loop.npz"))
+    B, K, V, eos, pad, bos, L = (int(v) for v in z["meta"])
+    script = torch.from_numpy(z["script"])
+
+    class ScriptedDecoder:
+        def __init__(self):
+            self.calls = 0
+
+        def prefill(self, ids, *a):
+            return self.step(ids)
+
+        def step(self, ids):
+            out = script[self.calls][:, None, :].clone()
+            self.calls += 1
+            return out
+
+    cfg = SimpleNamespace(num_codebooks=K, bos_token_id=bos, pad_token_id=pad, eos_token_id=eos)
+    enc = torch.zeros(B, 1, 8)
+    n = 0
+    while f"case{n}_seq" in z:
+        do_sample, min_new, top_k, seed = (int(v) for v in z[f"case{n}_cfg"])
+        temp, top_p = (float(v) for v in z[f"case{n}_fcfg"])
+        gen = dict(max_length=L, do_sample=bool(do_sample), min_new_tokens=min_new, temperature=temp, top_k=top_k, top_p=top_p)
+        dec = ScriptedDecoder()
+        if do_sample:
+            torch.manual_seed(seed)
+        out = generate_tokens(dec, cfg, enc, None, None, None, gen)
+        assert np.array_equal(out["raw_ids"], z[f"case{n}_seq"]), n
+        assert dec.calls == int(z[f"case{n}_calls"][0]), n
+        n += 1
+    assert n == 3
