@@ -511,3 +511,18 @@ def test_dac_decode_real_shape_bf16_tensor_core(monkeypatch):
     # bf16 storage between layers dominates both; the tensor-core path must be no worse than the FMA path
     assert e_tc < 0.1 * rms(ref) + 1e-3, (e_tc, rms(ref))
     assert e_tc < 1.5 * e_simt + 1e-3, (e_tc, e_simt)
+
+
+def test_fused_step_large_shape_single_tile_buffer(monkeypatch):
+    """Parler-TTS-Large layer shape (H=1536, F=6144, 24 heads; 2 layers): the fused kernel runs with ONE activation tile buffer,
+    a 96 KB weight slice per task and matrices whose tasks wrap around the grid (fc2: 192 tasks on 148 CTAs) -- the code
+    paths the Mini shape does not reach.  Same bar as the other shapes: bit-identical to the multi-kernel path.
+    (Added after the last GPU session of round 1: first exercised by the round-end run.)"""
+    from oracle.config import large_cfg
+    cfg = large_cfg(num_hidden_layers=2, max_position_embeddings=128)
+    w = make_decoder_weights(cfg, seed=84, head_std=0.2)
+    a_ids, a_log, a_launch = _free_run_bf16(cfg, w, 8, 12, 6, 14, True, monkeypatch)
+    b_ids, b_log, b_launch = _free_run_bf16(cfg, w, 8, 12, 6, 14, False, monkeypatch)
+    assert a_launch < b_launch / 3, (a_launch, b_launch)  # the fused kernel was really used
+    assert np.array_equal(a_ids, b_ids)
+    assert np.array_equal(a_log, b_log)
