@@ -49,6 +49,11 @@ struct ptts_session {
   long long* prof;
   bool fused;        // decode steps run as the single persistent kernel (step.cu) instead of 8L+3 kernels
   StepParams sp;
+  // EXPERIMENTAL (PTTS_PREFILL_TC=1): prefill linear layers as tcgen05 GEMMs (gemm_tc.cu).  Library-owned scratch: row-major
+  // copies of the layer matrices (unpacked from the fragment-ordered blob AFTER ptts_decoder_finalize) and the row statistics.
+  bool prefill_tc;
+  char* aux_w;       // [L][layer_stride] mirror of the blob's layer region, matrices row-major
+  float* row_stats;  // [max(B*(P+1), B*S)][2]
 };
 
 extern "C" {
@@ -176,6 +181,26 @@ int ptts_session_create(const ptts_decoder_config* cfg, const void* blob, void* 
   s->fused = false;
   s->prof = nullptr;
   s->launches = 0;
+  s->prefill_tc = false;
+  s->aux_w = nullptr;
+  s->row_stats = nullptr;
+  if (cfg->dtype == PTTS_BF16 && env_flag("PTTS_PREFILL_TC", false)) {  // experimental, see gemm_tc.cu
+    const DecoderLayout& L = s->L;
+    const int64_t rows = (int64_t)B * ((P + 1) > S ? (P + 1) : S);
+    if (cudaMalloc(&s->aux_w, (size_t)(L.layer_stride * L.L)) == cudaSuccess && cudaMalloc(&s->row_stats, (size_t)rows * 2 * sizeof(float)) == cudaSuccess) {
+      int e = PTTS_OK;
+      for (int i = 0; i < L.L && !e; i++) {
+        const int64_t lo = L.layer_stride * i;
+        const char* src = s->blob + L.layer0 + lo;
+        char* dst = s->aux_w + lo;
+        const struct { int64_t off; int64_t N; int K; } mats[7] = {{L.wqkv, L.qkv_rows, L.H}, {L.wo, L.H, L.H}, {L.wqc, L.H, L.H}, {L.wkvc, L.ckv_rows, L.H},
+                                                                   {L.woc, L.H, L.H}, {L.fc1, L.F, L.H}, {L.fc2, L.H, L.F}};
+        for (int m = 0; m < 7 && !e; m++) e = unpack_fragments(src + mats[m].off, dst + mats[m].off, mats[m].N, mats[m].K, nullptr);
+      }
+      s->prefill_tc = (e == PTTS_OK) && cudaDeviceSynchronize() == cudaSuccess;
+    }
+    if (!s->prefill_tc) { cudaFree(s->aux_w); cudaFree(s->row_stats); s->aux_w = nullptr; s->row_stats = nullptr; cudaGetLastError(); }
+  }
   *out = s;
   return PTTS_OK;
 }
@@ -184,6 +209,8 @@ int ptts_session_destroy(ptts_session* s) {
   if (!s) return PTTS_OK;
   if (s->exec) cudaGraphExecDestroy(s->exec);
   if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
+  if (s->aux_w) cudaFree(s->aux_w);
+  if (s->row_stats) cudaFree(s->row_stats);
   delete s;
   return PTTS_OK;
 }
@@ -332,6 +359,10 @@ static int run_forward(ptts_session* s, cudaStream_t st, bool prefill, const voi
     a.M = Mrows; a.N = N; a.K = K; a.Kc = (K > H && K % H == 0) ? H : K;
     a.epi = epi; a.act = c.activation; a.ctrl = ctrl;
     s->launches++;
+    if (prefill && s->prefill_tc && woff >= L.layer0 && woff < L.layer0 + L.layer_stride * L.L && linear_tc_supported(a)) {
+      if (a.c1 != nullptr) s->launches++;  // row statistics kernel
+      return launch_linear_tc(a, s->aux_w + (woff - L.layer0), s->row_stats, st);
+    }
     return launch_linear(a, c.dtype, st, pdl, s->sm_count);
   };
 

@@ -18,6 +18,10 @@ struct LinearArgs {
   const Ctrl* ctrl;            // device control block: kernels no-op once generation has finished
 };
 int launch_linear(const LinearArgs& a, int dtype, cudaStream_t st, bool pdl, int sm_count);
+// EXPERIMENTAL tcgen05 prefill GEMM (gemm_tc.cu; only reached with PTTS_PREFILL_TC=1)
+bool linear_tc_supported(const LinearArgs& a);
+int launch_linear_tc(const LinearArgs& a, const void* w_rowmajor, float* stats_scratch, cudaStream_t st);
+int unpack_fragments(const void* frag, void* dst_rowmajor, int64_t N, int K, cudaStream_t st);
 int pack_matrix(const void* src, int src_dtype, int64_t rows, int64_t cols, int row_off, int K, void* dst, int dst_dtype, cudaStream_t st);
 int fold_layernorm(void* w_packed, int N, int K, const float* gamma, const float* beta, float* c1, float* c2, cudaStream_t st);
 int pack_plain(const void* src, int src_dtype, int64_t n, void* dst, int dst_dtype, cudaStream_t st);

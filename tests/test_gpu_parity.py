@@ -513,6 +513,34 @@ def test_dac_decode_real_shape_bf16_tensor_core(monkeypatch):
     assert e_tc < 1.5 * e_simt + 1e-3, (e_tc, e_simt)
 
 
+@pytest.mark.skipif(os.environ.get("PTTS_TEST_PREFILL_TC") != "1",
+                    reason="experimental tcgen05 prefill GEMM (gemm_tc.cu), not validated on a GPU yet: enable with PTTS_TEST_PREFILL_TC=1")
+def test_prefill_tc_matches_default_prefill(monkeypatch):
+    """PTTS_PREFILL_TC=1 routes the prefill linear layers (M = B*(P+1) and B*S rows) through the tcgen05 GEMM; the first-step
+    logits must agree with the default path to bf16 accumulation-order noise and pick the same tokens where the margin is clear."""
+    cfg = mini_cfg(num_hidden_layers=2, max_position_embeddings=256)
+    w = make_decoder_weights(cfg, seed=85, head_std=0.2)
+    dcfg = tiny_dac_cfg(n_codebooks=cfg.num_codebooks, codebook_size=cfg.codebook_size)
+    B, S, P = 8, 32, 31   # 256 prompt rows, 256 encoder rows: two 128-row tiles each
+    enc, enc_mask, prompt, prompt_mask = synth_inputs(cfg, B, S, P, seed=5)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("PTTS_PREFILL_TC", flag)
+        model = build_product_model(cfg, dcfg, w, make_dac_weights(dcfg, seed=1), dtype=torch.bfloat16)
+        sess = model.decoder.engine.session(B, P, S, P + 8)
+        sess.begin(8, do_sample=False)
+        sess.prefill(prompt.to(DEV), prompt_mask, enc.to(DEV), enc_mask)
+        torch.cuda.synchronize()
+        out[flag] = sess.logits.float().cpu().numpy().copy()
+    a, b = out["1"], out["0"]
+    scale = np.abs(b).max()
+    assert np.isfinite(a).all()
+    assert np.abs(a - b).max() < 0.03 * scale, (np.abs(a - b).max(), scale)
+    srt = np.sort(b, -1)
+    clear = (srt[:, -1] - srt[:, -2]) > 0.03 * scale
+    assert np.array_equal(a.argmax(-1)[clear], b.argmax(-1)[clear])
+
+
 def test_fused_step_large_shape_single_tile_buffer(monkeypatch):
     """Parler-TTS-Large layer shape (H=1536, F=6144, 24 heads; 2 layers): the fused kernel runs with ONE activation tile buffer,
     a 96 KB weight slice per task and matrices whose tasks wrap around the grid (fc2: 192 tasks on 148 CTAs) -- the code
