@@ -180,7 +180,9 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "audio codec tokens/sec (all codebooks)", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Parler-TTS-Mini batch=32 top-k=50 decode (CPU port, bounded sample)", "sample": sample},
+            "config": {"workload": f"Parler-TTS-Mini bf16 batch={B_PER_GPU}/GPU {args.decode_steps} decode steps top-k=50 (BASELINE configs[1])",
+                       "global_batch": args.gpus * B_PER_GPU, "prompt_len": P_LEN, "desc_len": S_LEN, "parallelism": f"batch-shard x{args.gpus}",
+                       "sample": sample + " -- the reference's CPU code path computes in fp32; same shapes, prompt and description lengths"},
             "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
                              "os_cpu_count": os.cpu_count()},
             "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
