@@ -15,10 +15,11 @@ from .modeling import (
     apply_delay_pattern_mask,
     build_delay_pattern_mask,
 )
+from .incremental import IncrementalDecoder, dac_dependency_radius
 from .streamer import ParlerTTSStreamer
 
 __all__ = [
     "ParlerTTSConfig", "ParlerTTSDecoderConfig", "DACConfig", "DACModel", "GenerationConfig", "ParlerTTSForCausalLM",
     "ParlerTTSForConditionalGeneration", "ParlerTTSLogitsProcessor", "apply_delay_pattern_mask",
-    "build_delay_pattern_mask", "ParlerTTSStreamer",
+    "build_delay_pattern_mask", "ParlerTTSStreamer", "IncrementalDecoder", "dac_dependency_radius",
 ]

@@ -513,6 +513,25 @@ def test_dac_decode_real_shape_bf16_tensor_core(monkeypatch):
     assert e_tc < 1.5 * e_simt + 1e-3, (e_tc, e_simt)
 
 
+def test_streamer_incremental_equals_full_decode():
+    """ParlerTTSStreamer(incremental=True): chunks decoded from `new frames + receptive-field context` windows
+    concatenate to the waveform generate() returns from one decode of all frames.  (Host logic verified on the CPU against the
+    oracle DAC in tests/test_host_logic.py; added after the last GPU session of round 1: first exercised by the round-end run.)"""
+    from parler_tts_b200 import ParlerTTSStreamer
+    cfg, dcfg = tiny_cfg(), tiny_dac_cfg()
+    w = make_decoder_weights(cfg, seed=61, head_std=0.5)
+    model = build_product_model(cfg, dcfg, w, make_dac_weights(dcfg, seed=2), dtype=torch.float32)
+    enc, enc_mask, prompt, prompt_mask = synth_inputs(cfg, 1, 6, 3, seed=9, masks=False)
+    st = ParlerTTSStreamer(model, device=DEV, play_steps=6, incremental=True)
+    audio = model.generate(encoder_outputs=(enc.to(DEV),), prompt_hidden_states=prompt.to(DEV), do_sample=False, max_length=60,
+                           streamer=st, _suppress_special=True)
+    chunks = [c for c in st]
+    total = np.concatenate(chunks)
+    full = audio[0].float().cpu().numpy()
+    assert total.shape[0] == full.shape[0] and sum(len(c) > 0 for c in chunks) >= 2
+    assert np.abs(total - full).max() < 1e-4
+
+
 @pytest.mark.skipif(os.environ.get("PTTS_TEST_PREFILL_TC") != "1",
                     reason="experimental tcgen05 prefill GEMM (gemm_tc.cu), not validated on a GPU yet: enable with PTTS_TEST_PREFILL_TC=1")
 def test_prefill_tc_matches_default_prefill(monkeypatch):

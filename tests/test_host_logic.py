@@ -150,3 +150,87 @@ def test_layernorm_fold_algebra():
     rstd = 1.0 / np.sqrt(np.maximum(S2 / K - mean * mean, 0.0) + eps)
     got = rstd[:, None] * (x @ Wp.T - mean[:, None] * c1) + c2
     np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9)
+
+
+def test_incremental_codec_decode_equals_full_decode():
+    """parler_tts_b200.incremental (host logic) driven by the CPU oracle DAC as decode_fn: the concatenated
+    chunks equal one decode of the whole sequence; a radius one frame too small does not (so the derived radius is tight
+    enough to be meaningful)."""
+    from oracle.config import tiny_dac_cfg
+    from oracle.dac import OracleDAC
+    from oracle.weights import make_dac_weights
+    from parler_tts_b200.incremental import IncrementalDecoder, dac_dependency_radius
+    cfg = tiny_dac_cfg()
+    dac = OracleDAC(cfg, make_dac_weights(cfg, seed=4))
+    hop = int(np.prod(cfg.upsampling_ratios))
+    R = dac_dependency_radius(cfg.upsampling_ratios)
+    assert R == dac_dependency_radius([8, 8, 4, 2]) == 10        # the 44.1 kHz DAC stack
+    g = torch.Generator().manual_seed(0)
+    B, K, T = 2, cfg.n_codebooks, 61
+    codes = torch.randint(0, cfg.codebook_size, (B, K, T), generator=g)
+    decode_fn = lambda c: dac.decode(c[None])[:, 0]
+    full = decode_fn(codes)
+
+    def run(radius, chunks):
+        inc = IncrementalDecoder(decode_fn, hop, radius)
+        outs, t = [], 0
+        for n in chunks:
+            o = inc.push(codes[..., t:t + n]); t += n
+            if o is not None:
+                outs.append(o)
+        o = inc.finish()
+        if o is not None:
+            outs.append(o)
+        assert t == T
+        return torch.cat(outs, dim=-1), inc
+
+    for chunks in ([1] * T, [7, 3, 20, 1, 1, 12, 17], [T], [30, 31]):
+        got, inc = run(R, chunks)
+        assert got.shape == full.shape
+        assert torch.allclose(got, full, atol=5e-5, rtol=0), (chunks, float((got - full).abs().max()))  # fp reassociation of torch's conv only
+        assert inc.codes.shape[-1] <= R + max(chunks) + R      # bounded state: O(T) total work
+    short, _ = run(R - 4, [5] * 12 + [1])
+    assert float((short - full).abs().max()) > 1e-3
+
+
+def test_streamer_incremental_mode_emits_the_full_decode(monkeypatch):
+    """ParlerTTSStreamer(incremental=True): host logic only -- the CUDA delay-pattern ops and the DAC are replaced by the CPU
+    oracle, a scripted token stream stands in for generate().  The queued chunks concatenate to exactly one decode of all
+    frames, and no chunk is ever revised (the reference streamer re-decodes the whole history every `play_steps`)."""
+    from types import SimpleNamespace
+    import parler_tts_b200.streamer as S
+    from oracle.config import tiny_dac_cfg
+    from oracle.dac import OracleDAC
+    from oracle.weights import make_dac_weights
+    from oracle.delay_pattern import build_delay_pattern_mask as obuild, apply_delay_pattern_mask as oapply
+    monkeypatch.setattr(S, "build_delay_pattern_mask",
+                        lambda ids, bos, pad, L, K: tuple(torch.from_numpy(np.asarray(a)) for a in obuild(ids.numpy(), bos, pad, L, K)))
+    monkeypatch.setattr(S, "apply_delay_pattern_mask", lambda ids, m: torch.from_numpy(oapply(ids.numpy(), m.numpy())))
+    cfg = tiny_dac_cfg()
+    dac = OracleDAC(cfg, make_dac_weights(cfg, seed=6))
+    K, cs, bos, eos = cfg.n_codebooks, cfg.codebook_size, 65, 64
+    enc = SimpleNamespace(config=SimpleNamespace(codebook_size=cs, decoder_rates=list(cfg.upsampling_ratios), sampling_rate=44100, frame_rate=86),
+                          decode=lambda audio_codes, **kw: SimpleNamespace(audio_values=dac.decode(audio_codes)))
+    model = SimpleNamespace(decoder=SimpleNamespace(num_codebooks=K), audio_encoder=enc, device="cpu", use_audio_scales=False,
+                            use_4dim_audio_codes=False,
+                            generation_config=SimpleNamespace(bos_token_id=bos, pad_token_id=eos, decoder_start_token_id=bos))
+    F = 47
+    codes = torch.randint(0, cs, (1, K, F), generator=torch.Generator().manual_seed(2))
+    steps = F + K
+    raw = torch.full((K, 1 + steps), eos, dtype=torch.long)
+    raw[:, 0] = bos
+    for k in range(K):
+        for t in range(1, 1 + steps):
+            f = t - 1 - k
+            raw[k, t] = codes[0, k, f] if 0 <= f < F else (7 if f < 0 else eos)   # junk where the delay mask will put BOS
+    st = S.ParlerTTSStreamer(model, device="cpu", play_steps=5, incremental=True)
+    st.put(raw[:, :1])
+    for t in range(1, 1 + steps):
+        st.put(raw[:, t])
+    st.end()
+    chunks = list(st)
+    got = np.concatenate(chunks)
+    full = dac.decode(codes[None])[0, 0].numpy()
+    assert got.shape == full.shape
+    assert np.abs(got - full).max() < 5e-5
+    assert sum(len(c) > 0 for c in chunks) >= 4          # audio flowed while tokens were still arriving
