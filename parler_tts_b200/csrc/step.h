@@ -32,7 +32,8 @@ struct StepParams {
   int do_sample_phase;     // 1: logits -> token inside the kernel (ptts_decode_steps); 0: stop at the logits
   int sample_items;        // ceil(V / 32)
   int* progress;           // debug: last phase each CTA arrived at (printed on a barrier timeout)
-  int dbg;                 // PTTS_DBG experiment bits (1: no weight L2 prefetch, 2: no K/V prefetch)
+  int dbg;                 // PTTS_DBG measurement switches, all off by default (1: no weight L2 prefetch, 2: no K/V prefetch,
+                           // 4 / 8: omit the shared-memory proxy fence before the weight / tile copy -- timing experiments only)
   long long* prof;         // optional [(8L+3)][8] clock64 timestamps written by CTA 0 (debug / profiles)
 };
 
