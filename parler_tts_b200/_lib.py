@@ -11,7 +11,9 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libptts_b200.so")
+# PTTS_LIB selects an alternative in-tree build of the same ABI (csrc/build.py --tag <t> -> libptts_b200_<t>.so), so that several
+# kernel variants can be compared inside one GPU session; the default is the product library.
+LIB_PATH = os.environ.get("PTTS_LIB") or os.path.join(_HERE, "csrc", "libptts_b200.so")
 
 BF16, F32, I64, I32 = 0, 1, 2, 3
 OK, EINVAL, ECUDA, ESTATE = 0, 1, 2, 3

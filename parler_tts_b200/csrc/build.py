@@ -1,7 +1,9 @@
 """Build libptts_b200.so in-tree with nvcc for sm_100a (no torch / pybind dependency: pure C ABI).
 
-Usage: python parler_tts_b200/csrc/build.py [--force]
+Usage: python parler_tts_b200/csrc/build.py [--force] [--tag NAME -DMACRO ...]
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+`--tag NAME` builds a VARIANT (extra nvcc flags after it, e.g. -DPTTS_SOME_EXPERIMENT) into libptts_b200_NAME.so next to the
+product library without touching it; load it with PTTS_LIB=<path> (parler_tts_b200/_lib.py).
 """
 from __future__ import annotations
 import concurrent.futures as cf
@@ -58,5 +60,30 @@ def build(force: bool = False, verbose: bool = True) -> str:
     return LIB
 
 
+def build_variant(tag: str, extra_flags: list[str]) -> str:
+    """Compile every source with extra flags into build_<tag>/ and link libptts_b200_<tag>.so (the product .so is untouched)."""
+    out_dir = os.path.join(HERE, f"build_{tag}")
+    os.makedirs(out_dir, exist_ok=True)
+    lib = os.path.join(HERE, f"libptts_b200_{tag}.so")
+
+    def cc(src):
+        obj = os.path.join(out_dir, src.replace(".cu", ".o"))
+        r = subprocess.run([NVCC, *FLAGS, *extra_flags, "-c", os.path.join(HERE, src), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(cc, SOURCES))
+    r = subprocess.run([NVCC, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    if "--tag" in sys.argv:
+        i = sys.argv.index("--tag")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv))
