@@ -66,9 +66,13 @@ typedef struct ptts_gen_params {
   int32_t top_k;           /* 0 = off */
   float top_p;             /* >= 1 = off */
   float temperature;       /* 1 = off */
-  uint64_t seed;           /* Philox key; substream = (row, step): invariant to batch sharding */
+  uint64_t seed;           /* Philox key; substream = (row_base + row, step) */
   int32_t suppress_special; /* bench aid: mask ids >= codebook_size (never set by generate()) */
   int32_t codebook_size;
+  int32_t row_base;        /* global index of this session's first row (= first utterance * num_codebooks): with a batch
+                            * sharded over GPUs every shard passes its own offset, so the draws of an utterance do not
+                            * depend on the number of shards */
+  int32_t reserved_;
 } ptts_gen_params;
 
 /* Tensor ids for ptts_decoder_pack(). `index` = layer (per-layer tensors) or codebook (EMBED/LM_HEAD). */

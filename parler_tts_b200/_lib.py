@@ -29,7 +29,8 @@ class DecoderConfigC(C.Structure):
 class GenParamsC(C.Structure):
     _fields_ = [("max_length", C.c_int32), ("min_new_tokens", C.c_int32), ("do_sample", C.c_int32),
                 ("top_k", C.c_int32), ("top_p", C.c_float), ("temperature", C.c_float), ("seed", C.c_uint64),
-                ("suppress_special", C.c_int32), ("codebook_size", C.c_int32)]
+                ("suppress_special", C.c_int32), ("codebook_size", C.c_int32),
+                ("row_base", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class DacConfigC(C.Structure):

@@ -45,7 +45,11 @@ __device__ __forceinline__ int sample_row(const SampleArgs& p, const ptts_gen_pa
     {
       const int par = cur_len & 1;
       int fu = p.first_unf[par * p.B + b];
-      if (p.eos_seen[fu] > 0 && fu < b * p.K + p.K - 1) fu++;
+      // eos_seen[r] = 1 + column of row r's first EOS (0 = none).  The reference counts EOS over input_ids, i.e. columns
+      // < cur_len (logits_processors.py:46): an EOS written by another warp during THIS step (column cur_len) must not count,
+      // so the test is on the column, not on a flag (rows of one batch item are sampled by different warps / CTAs).
+      const int es = p.eos_seen[fu];
+      if (es > 0 && es <= cur_len && fu < b * p.K + p.K - 1) fu++;
       if (k == 0 && lane == 0) p.first_unf[(par ^ 1) * p.B + b] = fu;
       if (row > fu) mask_eos = true;
     }
@@ -108,7 +112,7 @@ __device__ __forceinline__ int sample_row(const SampleArgs& p, const ptts_gen_pa
         s = warp_sum(s);
       }
       // inverse-CDF draw in index order
-      const float target = philox_uniform(g.seed, (uint32_t)row, (uint32_t)cur_len) * s;
+      const float target = philox_uniform(g.seed, (uint32_t)(row + g.row_base), (uint32_t)cur_len) * s;
       float carry = 0.f;
       int found = -1, last_nz = -1;
 #pragma unroll
@@ -154,7 +158,7 @@ __device__ __forceinline__ int sample_row(const SampleArgs& p, const ptts_gen_pa
       const int unf = p.unfinished[row];
       if (!unf) tok = p.pad;  // next_tokens * unfinished + pad * (1 - unfinished)
       p.raw_ids[(size_t)row * p.raw_ld + cur_len] = tok;
-      if (tok == p.eos) p.eos_seen[row] = 1;
+      if (tok == p.eos && p.eos_seen[row] == 0) p.eos_seen[row] = cur_len + 1;
       const int new_len = cur_len + 1;
       const int done = (tok == p.eos) || (new_len >= g.max_length);
       still_unfinished = unf && !done;

@@ -120,7 +120,12 @@ class DACModel:
             self._c.strides[i] = int(s)
         self._c.dtype = _lib.dtype_code(dtype)
         self.hop_length = math.prod(config.decoder_rates)
-        self.blob = None
+        # the packed weight blob exists from construction on (zeros until load_state_dict / a broadcast fills it), so that
+        # every rank of a sharded run owns a buffer of the right size for the init broadcast (dist.broadcast_model_weights)
+        nbytes = C.c_int64()
+        _lib.check(_lib.lib().ptts_dac_blob_bytes(C.byref(self._c), C.byref(nbytes)))
+        self.blob = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
+        self.loaded = False
         self._ws = None
 
     # -- weights -----------------------------------------------------------------------------------
@@ -134,12 +139,10 @@ class DACModel:
         if missing and strict:
             raise ValueError(f"DACModel.load_state_dict: missing keys {missing[:5]}{'...' if len(missing) > 5 else ''}")
         lib = _lib.lib()
-        nbytes = C.c_int64()
-        _lib.check(lib.ptts_dac_blob_bytes(C.byref(self._c), C.byref(nbytes)))
         n = C.c_int32()
         _lib.check(lib.ptts_dac_num_tensors(C.byref(self._c), C.byref(n)))
         assert n.value == len(names), (n.value, len(names))
-        self.blob = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
+        self.blob.zero_()
         for i, name in enumerate(names):
             if name not in sd:
                 continue
@@ -150,6 +153,7 @@ class DACModel:
             _lib.check(lib.ptts_dac_pack(C.byref(self._c), _lib.ptr(self.blob), i, _lib.ptr(t), _lib.dtype_code(t.dtype),
                                          t.numel(), _lib.stream_ptr()))
         torch.cuda.current_stream().synchronize()  # staging tensors above go out of scope
+        self.loaded = True
         return self
 
     def to(self, *args, **kwargs):
@@ -165,7 +169,7 @@ class DACModel:
     @torch.no_grad()
     def decode(self, audio_codes, audio_scales=None, padding_mask=None, return_dict=None):
         """audio_codes [1, B, K, T] int64 (CUDA) -> DACDecoderOutput(audio_values [B, 1, hop*T])."""
-        if self.blob is None:
+        if not self.loaded:
             raise RuntimeError("DACModel has no weights loaded")
         if len(audio_codes) != 1:
             raise ValueError(f"Expected one frame, got {len(audio_codes)}")

@@ -3,7 +3,8 @@
 The path has no per-step exchange -- utterances are independent -- so the only collective is one
 broadcast of the packed weight blobs from rank 0 at init (NCCL over NVLink on GPUs; the same code runs
 on gloo/CPU tensors in the world_size-2 unit tests).  Sampling uses per-row Philox substreams keyed by
-the GLOBAL row index, so results do not depend on the number of shards.
+the GLOBAL row index (ptts_gen_params.row_base = first local utterance x num_codebooks; generate(row_base=...)
+or shard_row_base() below), so the draws of an utterance do not depend on the number of shards.
 """
 from __future__ import annotations
 import torch
@@ -15,6 +16,11 @@ def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_row_base(n: int, rank: int, world: int, num_codebooks: int) -> int:
+    """Global (utterance, codebook) row index of this rank's first row: the `row_base` to pass to generate()."""
+    return shard_range(n, rank, world)[0] * num_codebooks
 
 
 def shard_batch(tensors: dict, rank: int, world: int) -> dict:
@@ -31,13 +37,27 @@ def broadcast_blob(blob: torch.Tensor, src: int = 0, group=None) -> torch.Tensor
     return blob
 
 
+def model_weight_tensors(model) -> list[torch.Tensor]:
+    """Every device tensor that holds weights, in a fixed order that depends on the CONFIG only (never on what a rank has
+    loaded): the packed decoder blob, the packed DAC blob, the prompt embedding table and, when the text encoder's width
+    differs from the decoder's, enc_to_dec_proj (modeling_parler_tts.py:2388-2392).  All exist from construction on."""
+    ts = [model.decoder.engine.blob, model.audio_encoder.blob, model.embed_prompts_weight]
+    if model.enc_to_dec_proj is not None:
+        ts += list(model.enc_to_dec_proj)
+    return ts
+
+
 def broadcast_model_weights(model, src: int = 0, group=None):
-    """Rank `src` has loaded/packed the checkpoint; the others only allocated blobs of the same size."""
-    broadcast_blob(model.decoder.engine.blob, src, group)
-    if model.audio_encoder.blob is not None:
-        broadcast_blob(model.audio_encoder.blob, src, group)
-    if model.embed_prompts_weight is not None:
-        broadcast_blob(model.embed_prompts_weight, src, group)
+    """Rank `src` has loaded/packed the checkpoint; the others only constructed the model (zero-filled buffers of the same
+    sizes).  Every rank issues the same sequence of broadcasts: one per tensor of model_weight_tensors() plus one flag word."""
+    ts = model_weight_tensors(model)
+    for t in ts:
+        broadcast_blob(t, src, group)
+    flags = torch.tensor([int(model.audio_encoder.loaded), int(model._side_loaded)], dtype=torch.int32, device=ts[0].device)
+    broadcast_blob(flags, src, group)
+    loaded = flags.cpu().tolist()
+    model.audio_encoder.loaded = bool(loaded[0])
+    model._side_loaded = bool(loaded[1])
     return model
 
 

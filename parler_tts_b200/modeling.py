@@ -256,11 +256,12 @@ class GenSession:
         return n.value
 
     def begin(self, max_length: int, do_sample=False, temperature=1.0, top_k=0, top_p=1.0, min_new_tokens=0, seed=0,
-              suppress_special=False, codebook_size=1024):
+              suppress_special=False, codebook_size=1024, row_base=0):
         g = _lib.GenParamsC()
         g.max_length, g.min_new_tokens, g.do_sample = int(max_length), int(min_new_tokens or 0), int(bool(do_sample))
         g.top_k, g.top_p, g.temperature = int(top_k or 0), float(1.0 if top_p is None else top_p), float(temperature or 1.0)
         g.seed, g.suppress_special, g.codebook_size = int(seed) & (2 ** 64 - 1), int(bool(suppress_special)), int(codebook_size)
+        g.row_base = int(row_base)  # global row of this shard's first (utterance, codebook) stream: Philox substream key
         _lib.check(_lib.lib().ptts_generate_begin(self.h, C.byref(g), _lib.stream_ptr()))
         self.max_length = int(max_length)
 
@@ -347,8 +348,17 @@ class ParlerTTSForConditionalGeneration:
         self.prompt_cross_attention = config.prompt_cross_attention
         if self.prompt_cross_attention:
             raise ValueError("prompt_cross_attention=True checkpoints are not supported by the B200 path yet")
-        self.embed_prompts_weight: Optional[torch.Tensor] = None
+        # Side-input parameters exist (zero-filled) from construction on, with shapes that depend on the config only, so every
+        # rank of a sharded run issues the SAME list of broadcasts at init (dist.broadcast_model_weights); `_side_loaded`
+        # says whether they hold real weights.  enc_to_dec_proj exists iff the text encoder's width differs (:2388-2392).
+        dd = config.decoder
+        self.embed_prompts_weight: torch.Tensor = torch.zeros(config.vocab_size, dd.hidden_size, device=self.device, dtype=dtype)
+        te_hidden = (config.text_encoder or {}).get("d_model", (config.text_encoder or {}).get("hidden_size"))
         self.enc_to_dec_proj: Optional[tuple] = None
+        if te_hidden is not None and int(te_hidden) != dd.hidden_size:
+            self.enc_to_dec_proj = (torch.zeros(dd.hidden_size, int(te_hidden), device=self.device, dtype=dtype),
+                                    torch.zeros(dd.hidden_size, device=self.device, dtype=dtype))
+        self._side_loaded = False
         self.use_audio_scales = True   # DACModel.decode has an `audio_scales` parameter (:2416-2417)
         self.use_4dim_audio_codes = True  # dac_on_the_hub (:2419-2422, quirk Q14)
         d = config.decoder
@@ -359,10 +369,19 @@ class ParlerTTSForConditionalGeneration:
     # -- weights -----------------------------------------------------------------------------------
     def load_state_dict(self, sd: dict[str, torch.Tensor], dac_state_dict: Optional[dict] = None):
         self.decoder.engine.load_state_dict(sd, prefix="decoder.")
-        self.embed_prompts_weight = sd["embed_prompts.weight"].to(self.device, self.dtype)
+        if "embed_prompts.weight" in sd:
+            w = sd["embed_prompts.weight"].to(self.device, self.dtype)
+            if w.shape == self.embed_prompts_weight.shape:
+                self.embed_prompts_weight.copy_(w)
+            else:  # a checkpoint whose text vocabulary differs from config.vocab_size: follow the checkpoint
+                self.embed_prompts_weight = w.contiguous()
+            self._side_loaded = True
         if "enc_to_dec_proj.weight" in sd:
-            self.enc_to_dec_proj = (sd["enc_to_dec_proj.weight"].to(self.device, self.dtype),
-                                    sd["enc_to_dec_proj.bias"].to(self.device, self.dtype))
+            w, b = sd["enc_to_dec_proj.weight"].to(self.device, self.dtype), sd["enc_to_dec_proj.bias"].to(self.device, self.dtype)
+            if self.enc_to_dec_proj is not None and self.enc_to_dec_proj[0].shape == w.shape:
+                self.enc_to_dec_proj[0].copy_(w); self.enc_to_dec_proj[1].copy_(b)
+            else:
+                self.enc_to_dec_proj = (w.contiguous(), b.contiguous())
         ae = {k[len("audio_encoder."):]: v for k, v in sd.items() if k.startswith("audio_encoder.")}
         if dac_state_dict is not None:
             ae = dac_state_dict
@@ -452,7 +471,7 @@ class ParlerTTSForConditionalGeneration:
         B, S, _ = enc_hidden.shape
         prompt_hidden = mk.get("prompt_hidden_states")
         if prompt_hidden is None and mk.get("prompt_input_ids") is not None:
-            if self.embed_prompts_weight is None:
+            if not self._side_loaded:
                 raise ValueError("no embed_prompts weights loaded")
             prompt_hidden = torch.nn.functional.embedding(mk["prompt_input_ids"].to(self.device), self.embed_prompts_weight)
         prompt_mask = mk.get("prompt_attention_mask") if prompt_hidden is not None else None
