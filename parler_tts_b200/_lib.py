@@ -64,6 +64,7 @@ _SIGS = {
     "ptts_session_raw_ids": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_I32)]),
     "ptts_session_state": (C.c_int, [_VP, C.POINTER(_VP)]),
     "ptts_session_launches": (C.c_int, [_VP, C.POINTER(_I64)]),
+    "ptts_session_fused": (C.c_int, [_VP, C.POINTER(_I32)]),
     "ptts_session_set_profile": (C.c_int, [_VP, _VP]),
     "ptts_delay_build": (C.c_int, [_VP, _I32, _I32, _I32, _I64, _I64, _I32, _VP, _VP]),
     "ptts_delay_apply": (C.c_int, [_VP, _I32, _I32, _I64, _VP, _I64, _VP, _VP]),

@@ -244,12 +244,24 @@ static int pick_nt(int ntiles, int grid) {
   return 1;
 }
 
+// The fused kernel covers bf16, B <= 32, K <= 16: anything else runs the 8L+3-kernel path -- a 2x slower step.  Say so once per
+// process instead of degrading silently, and count it (ptts_session_fused reports which path a session uses).
+static bool fused_declined(ptts_session* s, const char* why) {
+  static bool warned = false;
+  if (!warned) {
+    fprintf(stderr, "ptts_b200: fused decode step not used for this session (B=%d, H=%d, K=%d: %s); decode steps run the multi-kernel path\n",
+            s->W.B, s->L.H, s->L.K, why);
+    warned = true;
+  }
+  return false;
+}
+
 static bool setup_fused(ptts_session* s) {
   const ptts_decoder_config& c = s->cfg;
   const DecoderLayout& L = s->L;
   const WorkspaceLayout& W = s->W;
-  if (c.dtype != PTTS_BF16 || W.B > 32 || L.K > 16 || !env_flag("PTTS_FUSED", true)) return false;
-  if (L.H % 64 != 0 || L.F % L.H != 0) return false;
+  if (c.dtype != PTTS_BF16 || !env_flag("PTTS_FUSED", true)) return false;
+  if (W.B > 32 || L.K > 16 || L.H % 64 != 0 || L.F % L.H != 0) return fused_declined(s, "batch > 32 rows, > 16 codebooks or an unsupported width");
   StepParams& p = s->sp;
   memset(&p, 0, sizeof(p));
   p.B = W.B; p.H = L.H; p.F = L.F; p.V = L.V; p.K = L.K; p.L = L.L; p.nh = L.nh; p.nkv = L.nkv; p.nckv = L.nckv;
@@ -291,15 +303,15 @@ static bool setup_fused(ptts_session* s) {
   const int64_t att = (int64_t)8 * (2 * 2 * 32 * 64 * 2 + 3 * 64 * 4) + 4 * 128 * 4;  // 8 x attn_decode_smem_per_warp<bf16>() + pair exchange
   const int64_t budget = 215 * 1024 - 2816;  // step.cu ST_HEADER
   p.nbuf = (2 * tile + wbytes <= budget) ? 2 : 1;
-  if (p.nbuf * tile < red) return false;
+  if (p.nbuf * tile < red) return fused_declined(s, "the K-reduction scratch does not fit the activation tile");
   p.wbuf_offset = align_up(p.nbuf * tile, 128);
   int64_t region = p.wbuf_offset + wbytes;
   if (att > region) region = att;
   region = align_up(region, 16);
-  if (region > budget) return false;  // does not fit: the multi-kernel path runs instead
+  if (region > budget) return fused_declined(s, "tile + weight slice exceed the shared memory of an SM");
   p.tile_region_bytes = region;
-  p.sample_items = (L.V + 31) / 32;
-  if (p.sample_items > 72) return false;
+  p.sample_items = (L.V + 255) / 256;
+  if (p.sample_items > 9) return fused_declined(s, "vocab_size > 2304");
   p.do_sample_phase = 1;
   p.prof = s->prof;
   { const char* d = getenv("PTTS_DBG"); p.dbg = d ? atoi(d) : 0; }
@@ -511,6 +523,7 @@ int ptts_session_set_profile(ptts_session* s, void* buf) {
   s->sp.prof = s->prof;
   return PTTS_OK;
 }
+int ptts_session_fused(ptts_session* s, int32_t* out) { PTTS_REQUIRE(s && out, "null"); *out = s->fused ? 1 : 0; return PTTS_OK; }
 int ptts_session_launches(ptts_session* s, int64_t* out) { PTTS_REQUIRE(s && out, "null"); *out = s->launches; return PTTS_OK; }
 
 // ---- stand-alone operators ----------------------------------------------------------------------

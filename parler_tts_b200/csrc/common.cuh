@@ -43,8 +43,7 @@ struct Ctrl {
   int steps_run;      // decode steps actually executed (not no-op'd)
   int launch_gen;     // fused step kernel launches so far (selects the barrier counter)
   int pad_[26];
-  unsigned bar[2];    // device-wide barrier counters of the fused step kernel (own 128 B line)
-  unsigned pad2_[30];
+  unsigned bar[32];   // barrier counters of the fused step kernel (own 128 B line): slot s uses bar[16 s + (launch_gen & 1)]
 };
 static_assert(sizeof(Ctrl) == 256, "Ctrl layout");
 

@@ -50,12 +50,13 @@ __device__ __forceinline__ void row_stat_mma(RowStatFrag& st, int mt, const uint
   mma_bf16_16816(st.sq[mt][1], a, a[1], a[3]);  // rows 8-15
 }
 
-// one warp's pass over its slabs kt = warp, warp + 8, ... of a staged [32][kt_count * 32] tile (row pitch in elements)
+// one warp's pass over its slabs kt = warp, warp + 8, ... of a staged [16 * MT][kt_count * 32] tile (row pitch in elements)
+template <int MT = 2>
 __device__ __forceinline__ void row_stat_pass(RowStatFrag& st, const bf16* xs, int pitch, int kt_count, int warp, int lane) {
   const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol = (lane >> 4) * 8;
   for (int kt = warp; kt < kt_count; kt += 8) {
 #pragma unroll
-    for (int mt = 0; mt < 2; mt++)
+    for (int mt = 0; mt < MT; mt++)
 #pragma unroll
       for (int j = 0; j < 2; j++) {
         uint32_t a[4];
@@ -66,11 +67,12 @@ __device__ __forceinline__ void row_stat_pass(RowStatFrag& st, const bf16* xs, i
   }
 }
 
-// part: shared float[8 warps][32 rows][2] -- this warp's partial (S1, S2) of every row
+// part: shared float[8 warps][32 rows][2] -- this warp's partial (S1, S2) of every row (rows 0..16*MT-1 are written)
+template <int MT = 2>
 __device__ __forceinline__ void row_stat_store(const RowStatFrag& st, float* part, int warp, int lane) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int mt = 0; mt < 2; mt++) {
+  for (int mt = 0; mt < MT; mt++) {
     float* pr = part + ((size_t)warp * 32 + mt * 16 + g) * 2;
     if (t == 0) { pr[0] = st.s1[mt][0]; pr[16] = st.s1[mt][2]; }
     if (t == (g >> 1)) {  // the thread holding the diagonal entries (g, g) and (g+8, g+8)

@@ -1,6 +1,6 @@
 // sample.cu -- logits -> next token, entirely on the device, plus the integer ops around it.
 //
-// One warp per row (B*K rows).  Replaces, per decode step:
+// One CTA per row (B*K rows; sample_core.cuh).  Replaces, per decode step:
 //   MinNewTokensLengthLogitsProcessor, ParlerTTSLogitsProcessor (logits_processors.py:44-53, stateful:
 //   quirk Q11), Temperature/TopK/TopP warpers, softmax + multinomial / argmax, finished-row padding,
 //   torch.cat of the history, EosTokenCriteria + MaxLengthCriteria, `unfinished.max()==0` (a host sync
@@ -16,20 +16,15 @@
 
 namespace ptts {
 
-constexpr int SAMPLE_WARPS = 4;
-
 template <int ITEMS>
-__global__ void __launch_bounds__(SAMPLE_WARPS * 32) sample_kernel(SampleArgs p, const int64_t* __restrict__ forced) {
+__global__ void __launch_bounds__(SMP_THREADS) sample_kernel(SampleArgs p, const int64_t* __restrict__ forced) {
   pdl_launch_dependents();
   pdl_wait();
   if (p.ctrl->active == 0) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * SAMPLE_WARPS + warp;
-  const int BK = p.B * p.K;
+  const int row = blockIdx.x;           // one CTA per (utterance, codebook) row
   const int cur_len = p.ctrl->cur_len;  // the new token becomes column `cur_len`
   const ptts_gen_params g = *p.gen;
-  int still_unfinished = 0;
-  if (row < BK) still_unfinished = sample_row<ITEMS>(p, g, forced, row, cur_len, lane);
+  sample_row_cta<ITEMS>(p, g, forced, row, cur_len);
   // last block advances the control block
   __threadfence();
   __syncthreads();
@@ -51,19 +46,19 @@ __global__ void __launch_bounds__(SAMPLE_WARPS * 32) sample_kernel(SampleArgs p,
 int launch_sample(const SampleArgs& a, const int64_t* forced, cudaStream_t st, bool pdl) {
   const int BK = a.B * a.K;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((BK + SAMPLE_WARPS - 1) / SAMPLE_WARPS);
-  cfg.blockDim = dim3(SAMPLE_WARPS * 32);
+  cfg.gridDim = dim3(BK);
+  cfg.blockDim = dim3(SMP_THREADS);
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl ? 1 : 0;
-  const int items = (a.V + 31) / 32;
-  PTTS_REQUIRE(items <= 72, "sample: vocab_size %d > 2304 not supported", a.V);
-  if (items <= 4) PTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sample_kernel<4>, a, forced));
-  else if (items <= 36) PTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sample_kernel<36>, a, forced));
-  else PTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sample_kernel<72>, a, forced));
+  const int items = (a.V + SMP_THREADS - 1) / SMP_THREADS;
+  PTTS_REQUIRE(items <= 9, "sample: vocab_size %d > 2304 not supported", a.V);
+  if (items <= 1) PTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sample_kernel<1>, a, forced));
+  else if (items <= 5) PTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sample_kernel<5>, a, forced));
+  else PTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sample_kernel<9>, a, forced));
   return PTTS_OK;
 }
 
@@ -72,7 +67,8 @@ __global__ void generate_begin_kernel(SampleArgs p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
     p.ctrl->cur_len = 1; p.ctrl->active = 1; p.ctrl->n_unfinished = 0; p.ctrl->done_blocks = 0; p.ctrl->steps_run = 0;
-    p.ctrl->launch_gen = 0; p.ctrl->bar[0] = 0; p.ctrl->bar[1] = 0;
+    p.ctrl->launch_gen = 0;
+    for (int j = 0; j < 32; j++) p.ctrl->bar[j] = 0;
   }
   if (i < BK) {
     p.raw_ids[(size_t)i * p.raw_ld] = p.bos;

@@ -412,10 +412,10 @@ __device__ __forceinline__ void attn_phase(const StepParams& p, Smem& sm, const 
     attention_decode_item_warp<bf16>(a, it / nkv, it % nkv, pos, region, bars, lane, att_parity, part, 2, xch, pair + 1);
 }
 
+// one CTA per (utterance, codebook) row (sample_core.cuh): 288 rows over 148 CTAs at Mini / batch 32
 template <int ITEMS>
 __device__ __noinline__ void sample_phase(const SampleArgs& sa, const ptts_gen_params& gp, int BK, int cur_len) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int row = blockIdx.x * ST_WARPS + warp; row < BK; row += gridDim.x * ST_WARPS) sample_row<ITEMS>(sa, gp, nullptr, row, cur_len, lane);
+  for (int row = blockIdx.x; row < BK; row += gridDim.x) sample_row_cta<ITEMS>(sa, gp, nullptr, row, cur_len);
 }
 
 template <int ITEMS>
@@ -633,11 +633,11 @@ int launch_decode_step(const StepParams& p, int grid, cudaStream_t st) {
   const int smem = step_smem_bytes(p);
   void* args[] = {(void*)&p};
   const void* fn;
-  if (p.sample_items <= 4) fn = (const void*)decode_step_kernel<4>;
-  else if (p.sample_items <= 36) fn = (const void*)decode_step_kernel<36>;
-  else fn = (const void*)decode_step_kernel<72>;
+  if (p.sample_items <= 1) fn = (const void*)decode_step_kernel<1>;
+  else if (p.sample_items <= 5) fn = (const void*)decode_step_kernel<5>;
+  else fn = (const void*)decode_step_kernel<9>;
   static int attr_done[3] = {0, 0, 0};
-  const int fi = p.sample_items <= 4 ? 0 : (p.sample_items <= 36 ? 1 : 2);
+  const int fi = p.sample_items <= 1 ? 0 : (p.sample_items <= 5 ? 1 : 2);
   if (!attr_done[fi]) {
     PTTS_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done[fi] = 1;

@@ -30,7 +30,7 @@ struct StepParams {
   int64_t tile_region_bytes;   // scratch after the header: [activation tiles | weight buffer], aliased by attention
   int64_t wbuf_offset;         // weight buffer offset inside the scratch region
   int do_sample_phase;     // 1: logits -> token inside the kernel (ptts_decode_steps); 0: stop at the logits
-  int sample_items;        // ceil(V / 32)
+  int sample_items;        // ceil(V / 256): logits per thread of the one-CTA-per-row sampler
   int* progress;           // debug: last phase each CTA arrived at (printed on a barrier timeout)
   int dbg;                 // PTTS_DBG measurement switches, all off by default (1: no weight L2 prefetch, 2: no K/V prefetch,
                            // 4 / 8: omit the shared-memory proxy fence before the weight / tile copy -- timing experiments only)

@@ -210,6 +210,7 @@ class GenSession:
         self.h = h
         self.K, self.V = eng.cfg.num_codebooks, eng.cfg.vocab_size
         self._keep: list[Any] = []
+        self._forced = None
 
     def close(self):
         if self.h is not None:
@@ -255,6 +256,13 @@ class GenSession:
         _lib.check(_lib.lib().ptts_session_launches(self.h, C.byref(n)))
         return n.value
 
+    @property
+    def fused(self) -> int:
+        """0: decode steps use the multi-kernel path; 1: the fused persistent step kernel (one launch per token)."""
+        n = C.c_int32()
+        _lib.check(_lib.lib().ptts_session_fused(self.h, C.byref(n)))
+        return n.value
+
     def begin(self, max_length: int, do_sample=False, temperature=1.0, top_k=0, top_p=1.0, min_new_tokens=0, seed=0,
               suppress_special=False, codebook_size=1024, row_base=0):
         g = _lib.GenParamsC()
@@ -288,7 +296,7 @@ class GenSession:
 
     def sample(self, forced: Optional[torch.Tensor] = None):
         f = None if forced is None else forced.to(device=self.eng.device, dtype=torch.int64).contiguous()
-        self._keep.append(f)
+        self._forced = f   # keep the staging tensor alive until the next call (the launch is asynchronous); never accumulates
         _lib.check(_lib.lib().ptts_sample(self.h, _lib.ptr(f), _lib.stream_ptr()))
 
     def decode_steps(self, n: int):
@@ -336,6 +344,14 @@ class ParlerTTSForConditionalGeneration:
 
     config_class = ParlerTTSConfig
     main_input_name = "input_ids"
+    # model kwargs generate() understands (reference: _validate_model_kwargs over forward()'s signature)
+    _MODEL_KWARGS = frozenset({"input_ids", "attention_mask", "prompt_input_ids", "prompt_attention_mask", "prompt_hidden_states",
+                               "encoder_outputs", "input_values", "decoder_input_ids", "padding_mask", "use_cache",
+                               "cache_implementation", "output_attentions", "output_hidden_states", "output_scores"})
+    # GenerationConfig fields the device loop does not implement, with the value that means "off"
+    _NEUTRAL_GENERATION_KNOBS = {"num_return_sequences": 1, "num_beam_groups": 1, "repetition_penalty": 1.0, "no_repeat_ngram_size": 0,
+                                 "length_penalty": 1.0, "typical_p": 1.0, "epsilon_cutoff": 0.0, "eta_cutoff": 0.0, "min_length": 0,
+                                 "penalty_alpha": None, "bad_words_ids": None, "force_words_ids": None, "guidance_scale": None}
 
     def __init__(self, config: ParlerTTSConfig, device="cuda", dtype=torch.bfloat16, text_encoder=None):
         if not isinstance(config, ParlerTTSConfig):
@@ -444,10 +460,22 @@ class ParlerTTSForConditionalGeneration:
         import copy
         gc = copy.deepcopy(generation_config if generation_config is not None else self.generation_config)
         seed = kwargs.pop("seed", 0)
+        row_base = kwargs.pop("row_base", 0)   # batch shards: global (utterance x codebook) row of this shard's first row (dist.py)
         return_codes = kwargs.pop("return_codes", False)
         suppress_special = kwargs.pop("_suppress_special", False)
         user_max_length = kwargs.get("max_length")
         mk = gc.update(**kwargs)
+        # The reference would honour (or reject) every generation knob; silently dropping one changes the output without an error.
+        unknown = sorted(k for k in mk if k not in self._MODEL_KWARGS)
+        if unknown:
+            raise ValueError(f"The following `model_kwargs` are not used by the model: {unknown} (note: typos in the generate "
+                             "arguments will also show up in this list)")
+        for k in ("use_cache", "cache_implementation", "output_attentions", "output_hidden_states", "output_scores"):
+            mk.pop(k, None)   # accepted for call compatibility: the device loop always uses its static cache
+        unsupported = {k: getattr(gc, k) for k, neutral in self._NEUTRAL_GENERATION_KNOBS.items() if getattr(gc, k, neutral) != neutral}
+        if unsupported:
+            raise ValueError(f"generation options {unsupported} are not supported by the B200 device loop "
+                             "(greedy / temperature / top-k / top-p sampling with min_new_tokens only)")
         if gc.num_beams != 1:
             raise ValueError("Got incompatible mode for generation, should be one of greedy or sampling. "
                              "Ensure that beam search is de-activated by setting `num_beams=1` and `num_beam_groups=1`.")
@@ -489,7 +517,7 @@ class ParlerTTSForConditionalGeneration:
         sess = self.decoder.engine.session(B, P, S, P + max_length)
         sess.begin(max_length, do_sample=gc.do_sample, temperature=gc.temperature, top_k=gc.top_k if gc.do_sample else 0,
                    top_p=gc.top_p, min_new_tokens=gc.min_new_tokens or 0, seed=seed, suppress_special=suppress_special,
-                   codebook_size=self.config.audio_encoder.codebook_size)
+                   codebook_size=self.config.audio_encoder.codebook_size, row_base=row_base)
         if streamer is not None:
             delayed = torch.full((B * K, 1), d.bos_token_id, dtype=torch.int64)
             streamer.put(delayed)
