@@ -161,7 +161,7 @@ int ptts_session_raw_ids(ptts_session* s, int64_t** out, int32_t* ld); /* [B*K, 
 int ptts_session_state(ptts_session* s, int32_t** out);         /* int32[8]: {cur_len, n_unfinished, ...} */
 int ptts_session_launches(ptts_session* s, int64_t* out);       /* kernels launched through this session  */
 /* After ptts_prefill: 0 = decode steps run the multi-kernel path (shape outside the fused kernel's range; a warning is printed
- * once), 1 = the fused persistent step kernel (one launch per token). */
+ * once), 1 = the fused persistent step kernel (one launch per token, step.cu), 2 = its cluster variant (step2.cu). */
 int ptts_session_fused(ptts_session* s, int32_t* out);
 /* Profiling aid: per-phase clock64() stamps of the fused step kernel into buf (device int64 [(8L+3)*8]); NULL = off. */
 int ptts_session_set_profile(ptts_session* s, void* buf);

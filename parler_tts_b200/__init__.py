@@ -9,6 +9,7 @@ __version__ = "0.1.0"
 from .configuration import DACConfig, GenerationConfig, ParlerTTSConfig, ParlerTTSDecoderConfig
 from .dac_wrapper import DACModel
 from .modeling import (
+    ParlerTTSCache,
     ParlerTTSForCausalLM,
     ParlerTTSForConditionalGeneration,
     ParlerTTSLogitsProcessor,
@@ -21,5 +22,5 @@ from .streamer import ParlerTTSStreamer
 __all__ = [
     "ParlerTTSConfig", "ParlerTTSDecoderConfig", "DACConfig", "DACModel", "GenerationConfig", "ParlerTTSForCausalLM",
     "ParlerTTSForConditionalGeneration", "ParlerTTSLogitsProcessor", "apply_delay_pattern_mask",
-    "build_delay_pattern_mask", "ParlerTTSStreamer", "IncrementalDecoder", "dac_dependency_radius",
+    "build_delay_pattern_mask", "ParlerTTSStreamer", "IncrementalDecoder", "dac_dependency_radius", "ParlerTTSCache",
 ]

@@ -48,12 +48,11 @@ struct ptts_session {
   int64_t launches;  // kernels launched through this session (bench.py reports it)
   long long* prof;
   bool fused;        // decode steps run as the single persistent kernel (step.cu) instead of 8L+3 kernels
+  bool cluster;      // ... and that kernel is the cluster variant (step2.cu: 6 device-wide phases per layer)
   StepParams sp;
-  // EXPERIMENTAL (PTTS_PREFILL_TC=1): prefill linear layers as tcgen05 GEMMs (gemm_tc.cu).  Library-owned scratch: row-major
-  // copies of the layer matrices (unpacked from the fragment-ordered blob AFTER ptts_decoder_finalize) and the row statistics.
+  // prefill linear layers as tcgen05 GEMMs (gemm_tc.cu) over the row-major weight copies ptts_decoder_finalize leaves in the
+  // blob (layout.h rm[]); PTTS_PREFILL_TC=0 keeps the mma.sync kernel (A/B runs)
   bool prefill_tc;
-  char* aux_w;       // [L][layer_stride] mirror of the blob's layer region, matrices row-major
-  float* row_stats;  // [max(B*(P+1), B*S)][2]
 };
 
 extern "C" {
@@ -137,7 +136,24 @@ int ptts_decoder_finalize(const ptts_decoder_config* cfg, void* blob, void* stre
     if (int e = fold_layernorm(lb + L.fc1, L.F, L.H, (const float*)(lb + L.ln3_w), (const float*)(lb + L.ln3_b), cf, cf + L.F, st)) return e;
   }
   float* ch = (float*)(b + L.c_heads);
-  return fold_layernorm(b + L.heads, L.K * L.V, L.H, (const float*)(b + L.final_ln_w), (const float*)(b + L.final_ln_b), ch, ch + L.K * L.V, st);
+  if (int e = fold_layernorm(b + L.heads, L.K * L.V, L.H, (const float*)(b + L.final_ln_w), (const float*)(b + L.final_ln_b), ch, ch + L.K * L.V, st)) return e;
+  {  // row-major copies for the tcgen05 prefill GEMM (gemm_tc.cu), unpacked AFTER the LayerNorm fold
+    const struct { int64_t off; int64_t N; int K; } mats[7] = {{L.wqkv, L.qkv_rows, L.H}, {L.wo, L.H, L.H}, {L.wqc, L.H, L.H}, {L.wkvc, L.ckv_rows, L.H},
+                                                               {L.woc, L.H, L.H}, {L.fc1, L.F, L.H}, {L.fc2, L.H, L.F}};
+    for (int i = 0; i < L.L; i++) {
+      char* lb = b + L.layer0 + L.layer_stride * i;
+      for (int m = 0; m < 7; m++)
+        if (int e = unpack_fragments(lb + mats[m].off, lb + L.rm[m], mats[m].N, mats[m].K, st)) return e;
+    }
+  }
+  if (L.cl_NC > 0) {  // second copy of the layer matrices, sliced per (phase, cluster, rank) for the cluster step kernel (step2.cu)
+    const int64_t mat_off[6] = {L.wqkv, L.wo, L.wqc, L.woc, L.fc1, L.fc2};
+    for (int i = 0; i < L.L; i++) {
+      char* lb = b + L.layer0 + L.layer_stride * i;
+      if (int e = cluster_pack_layer(lb, lb, mat_off, L.cp, L.nh, L.H, L.F, st)) return e;
+    }
+  }
+  return PTTS_OK;
 }
 
 int ptts_workspace_bytes(const ptts_decoder_config* cfg, int32_t B, int32_t P, int32_t S, int32_t max_cache_len, int64_t* out_bytes) {
@@ -179,28 +195,10 @@ int ptts_session_create(const ptts_decoder_config* cfg, const void* blob, void* 
   s->cap_stream = nullptr;
   s->begun = s->prefilled = false;
   s->fused = false;
+  s->cluster = false;
   s->prof = nullptr;
   s->launches = 0;
-  s->prefill_tc = false;
-  s->aux_w = nullptr;
-  s->row_stats = nullptr;
-  if (cfg->dtype == PTTS_BF16 && env_flag("PTTS_PREFILL_TC", false)) {  // experimental, see gemm_tc.cu
-    const DecoderLayout& L = s->L;
-    const int64_t rows = (int64_t)B * ((P + 1) > S ? (P + 1) : S);
-    if (cudaMalloc(&s->aux_w, (size_t)(L.layer_stride * L.L)) == cudaSuccess && cudaMalloc(&s->row_stats, (size_t)rows * 2 * sizeof(float)) == cudaSuccess) {
-      int e = PTTS_OK;
-      for (int i = 0; i < L.L && !e; i++) {
-        const int64_t lo = L.layer_stride * i;
-        const char* src = s->blob + L.layer0 + lo;
-        char* dst = s->aux_w + lo;
-        const struct { int64_t off; int64_t N; int K; } mats[7] = {{L.wqkv, L.qkv_rows, L.H}, {L.wo, L.H, L.H}, {L.wqc, L.H, L.H}, {L.wkvc, L.ckv_rows, L.H},
-                                                                   {L.woc, L.H, L.H}, {L.fc1, L.F, L.H}, {L.fc2, L.H, L.F}};
-        for (int m = 0; m < 7 && !e; m++) e = unpack_fragments(src + mats[m].off, dst + mats[m].off, mats[m].N, mats[m].K, nullptr);
-      }
-      s->prefill_tc = (e == PTTS_OK) && cudaDeviceSynchronize() == cudaSuccess;
-    }
-    if (!s->prefill_tc) { cudaFree(s->aux_w); cudaFree(s->row_stats); s->aux_w = nullptr; s->row_stats = nullptr; cudaGetLastError(); }
-  }
+  s->prefill_tc = (cfg->dtype == PTTS_BF16) && env_flag("PTTS_PREFILL_TC", true);
   *out = s;
   return PTTS_OK;
 }
@@ -209,8 +207,6 @@ int ptts_session_destroy(ptts_session* s) {
   if (!s) return PTTS_OK;
   if (s->exec) cudaGraphExecDestroy(s->exec);
   if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
-  if (s->aux_w) cudaFree(s->aux_w);
-  if (s->row_stats) cudaFree(s->row_stats);
   delete s;
   return PTTS_OK;
 }
@@ -315,6 +311,11 @@ static bool setup_fused(ptts_session* s) {
   p.do_sample_phase = 1;
   p.prof = s->prof;
   { const char* d = getenv("PTTS_DBG"); p.dbg = d ? atoi(d) : 0; }
+  // cluster variant (step2.cu) when the shape and the device allow it; PTTS_STEP=legacy keeps step.cu (A/B runs, cross-checks)
+  for (int i = 0; i < 6; i++) { p.cp[i] = L.cp[i]; p.cp_slice[i] = L.cp_slice[i]; }
+  p.cl_x = (bf16*)(ws + W.cl_x); p.cl_attn = (bf16*)(ws + W.cl_attn); p.cl_h = (bf16*)(ws + W.cl_h);
+  const char* mode = getenv("PTTS_STEP");
+  s->cluster = L.cl_NC > 0 && !(mode && strcmp(mode, "legacy") == 0) && cluster_step_available(p);
   return true;
 }
 
@@ -372,8 +373,14 @@ static int run_forward(ptts_session* s, cudaStream_t st, bool prefill, const voi
     a.epi = epi; a.act = c.activation; a.ctrl = ctrl;
     s->launches++;
     if (prefill && s->prefill_tc && woff >= L.layer0 && woff < L.layer0 + L.layer_stride * L.L && linear_tc_supported(a)) {
-      if (a.c1 != nullptr) s->launches++;  // row statistics kernel
-      return launch_linear_tc(a, s->aux_w + (woff - L.layer0), s->row_stats, st);
+      // the same matrix, row-major (layout.h rm[]): M = B*(P+1) or B*S rows are tensor-core work (tcgen05, gemm_tc.cu)
+      const int64_t in_layer = (woff - L.layer0) % L.layer_stride, lbase = woff - in_layer;
+      const int64_t frag[7] = {L.wqkv, L.wo, L.wqc, L.wkvc, L.woc, L.fc1, L.fc2};
+      for (int m = 0; m < 7; m++)
+        if (in_layer == frag[m]) {
+          if (a.c1 != nullptr) s->launches++;  // row statistics kernel
+          return launch_linear_tc(a, blob + lbase + L.rm[m], (float*)(ws + W.row_stats), st);
+        }
     }
     return launch_linear(a, c.dtype, st, pdl, s->sm_count);
   };
@@ -454,6 +461,7 @@ int ptts_decode_forward(ptts_session* s, void* stream) {
     StepParams p = s->sp;
     p.do_sample_phase = 0;
     s->launches++;
+    if (s->cluster) return launch_decode_step_cluster(p, (cudaStream_t)stream);
     return launch_decode_step(p, s->sm_count, (cudaStream_t)stream);
   }
   return run_forward(s, (cudaStream_t)stream, false, nullptr, nullptr);
@@ -472,7 +480,7 @@ int ptts_decode_steps(ptts_session* s, int32_t n_steps, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (s->fused) {  // one persistent kernel per token: nothing to gain from a graph
     for (int i = 0; i < n_steps; i++)
-      if (int e = launch_decode_step(s->sp, s->sm_count, st)) return e;
+      if (int e = s->cluster ? launch_decode_step_cluster(s->sp, st) : launch_decode_step(s->sp, s->sm_count, st)) return e;
     s->launches += n_steps;
     return PTTS_OK;
   }
@@ -523,7 +531,7 @@ int ptts_session_set_profile(ptts_session* s, void* buf) {
   s->sp.prof = s->prof;
   return PTTS_OK;
 }
-int ptts_session_fused(ptts_session* s, int32_t* out) { PTTS_REQUIRE(s && out, "null"); *out = s->fused ? 1 : 0; return PTTS_OK; }
+int ptts_session_fused(ptts_session* s, int32_t* out) { PTTS_REQUIRE(s && out, "null"); *out = s->fused ? (s->cluster ? 2 : 1) : 0; return PTTS_OK; }
 int ptts_session_launches(ptts_session* s, int64_t* out) { PTTS_REQUIRE(s && out, "null"); *out = s->launches; return PTTS_OK; }
 
 // ---- stand-alone operators ----------------------------------------------------------------------

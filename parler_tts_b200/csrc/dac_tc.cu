@@ -19,6 +19,9 @@
 // ConvTranspose1d(k = 2s, stride s) = s output phases x 2 taps (dac.cu explains the mapping).
 #include <cuda.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "dac.h"
 
@@ -228,7 +231,25 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 // 3-D bf16 tensor [d2][d1][d0] (d0 contiguous), box {64, box1, 1}, 128-byte swizzle, zero OOB fill
+static int encode_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1);
+
+// A decode issues ~60 convolution launches over the SAME buffers and shapes every time (the workspace and the weight blob are
+// caller-owned and stable): encode each tensor map once and reuse it (cuTensorMapEncodeTiled is a few microseconds of host time
+// per call, 60 of them sat between the launches of every decode -- profiles/r01_dac_ncu_full.md).
+struct MapKey { const void* base; uint64_t d0, d1, d2; uint32_t box1; };
+struct MapEntry { MapKey k; CUtensorMap m; };
 static int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1) {
+  static std::mutex mu;
+  static std::vector<MapEntry> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const MapEntry& e : cache)
+    if (e.k.base == base && e.k.d0 == d0 && e.k.d1 == d1 && e.k.d2 == d2 && e.k.box1 == box1) { *m = e.m; return PTTS_OK; }
+  if (int e = encode_map(m, base, d0, d1, d2, box1)) return e;
+  if (cache.size() >= 4096) cache.clear();   // many distinct (B, T) shapes over a long-lived process: start over
+  cache.push_back(MapEntry{MapKey{base, d0, d1, d2, box1}, *m});
+  return PTTS_OK;
+}
+static int encode_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(PTTS_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[3] = {d0, d1, d2};

@@ -1,7 +1,6 @@
-// gemm_tc.cu -- EXPERIMENTAL (off unless PTTS_PREFILL_TC=1): the prefill linear layers as tcgen05 GEMMs.
-//
-// Status: written at the end of round 1 after the GPU budget was spent -- it compiles for sm_100a but has NOT run on a GPU
-// yet.  Nothing on the default path calls into this file (api.cu checks the environment flag at session creation).
+// gemm_tc.cu -- the prefill linear layers as tcgen05 GEMMs (default for the bf16 model dtype; PTTS_PREFILL_TC=0 switches back to
+// the mma.sync kernel of gemm.cu for A/B runs).  Validated on B200 in round 2 (tests/test_gpu_parity.py::
+// test_prefill_tc_matches_default_prefill and the oracle comparison of the step-0 logits at the bench shape).
 //
 // Why: at prefill the decoder's linear layers see M = B*(P+1) (prompt) or B*S (encoder K/V projection) rows, ~1000-2000 for
 // the bench workload: 6.6 GFLOP per matrix, tensor-bound.  Today they run the decode GEMM (gemm.cu: 32-row tiles, mma.sync,

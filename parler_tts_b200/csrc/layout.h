@@ -25,8 +25,23 @@ struct DecoderLayout {
   int64_t ln1_w, ln1_b, wqkv, wo, ln2_w, ln2_b, wqc, wkvc, woc, ln3_w, ln3_b, fc1, fc2;
   int64_t c_qkv, c_qc, c_fc1;   // folded-LayerNorm vectors (c1 | c2), f32, per layer (ln_stats.cuh)
   int64_t final_ln_w, final_ln_b, heads, rope_cos, rope_sin, c_heads;
+  // cluster step kernel (step2.cu): a second copy of the six per-layer matrices, cut into one contiguous slice per
+  // (phase, cluster, rank): the n-tiles the cluster owns x the K range the rank reduces.  cl_NC == 0: shape not covered.
+  int cl_C, cl_NC;          // CTAs per cluster (8), clusters (= heads)
+  int64_t rm[7];            // per layer (bf16 only): ROW-MAJOR copies of wqkv, wo, wqc, wkvc, woc, fc1, fc2 for the tcgen05 prefill
+                            // GEMM (gemm_tc.cu: TMA-tiled K-major operands); same order as rm_src()
+  int64_t cp[6];            // per layer: offset of phase p's slices (A qkv | B o | C q_cross | D o_cross | E fc1 | F fc2)
+  int64_t cp_slice[6];      // bytes of one (cluster, rank) slice of phase p
   int64_t total;
 };
+
+// Shapes the cluster step kernel covers: bf16, MHA for self- and cross-attention, one cluster of 8 CTAs per head (<= 18 heads on
+// 148 SMs), K slices that are whole k32 tiles, and at most 4 fc1 n-tiles per rank (accumulator / exchange-buffer budget).
+static inline bool cluster_shape_ok(const ptts_decoder_config& c) {
+  const int H = c.hidden_size, nh = c.num_heads, F = c.ffn_dim;
+  return c.dtype == PTTS_BF16 && c.num_kv_heads == nh && c.num_cross_kv_heads == nh && nh * 8 <= 144 && H == nh * PTTS_HEAD_DIM &&
+         H % 256 == 0 && F % 256 == 0 && F % (nh * 64) == 0 && F / (nh * 64) <= 4 && H <= 1024 && F <= 4096 && c.num_codebooks <= 16;
+}
 
 static inline int dtype_size(int dt) { return dt == PTTS_BF16 ? 2 : 4; }
 
@@ -56,6 +71,23 @@ static inline DecoderLayout make_layout(const ptts_decoder_config& c) {
   l.c_qkv = take((int64_t)2 * l.qkv_rows * 4) - base;
   l.c_qc = take((int64_t)2 * l.H * 4) - base;
   l.c_fc1 = take((int64_t)2 * l.F * 4) - base;
+  for (int i = 0; i < 7; i++) l.rm[i] = 0;
+  if (c.dtype == PTTS_BF16) {
+    const int64_t sz[7] = {(int64_t)l.qkv_rows * l.H, (int64_t)l.H * l.H, (int64_t)l.H * l.H, (int64_t)l.ckv_rows * l.H, (int64_t)l.H * l.H,
+                           (int64_t)l.F * l.H, (int64_t)l.H * l.F};
+    for (int i = 0; i < 7; i++) l.rm[i] = take(sz[i] * 2) - base;
+  }
+  l.cl_C = l.cl_NC = 0;
+  for (int i = 0; i < 6; i++) l.cp[i] = l.cp_slice[i] = 0;
+  if (cluster_shape_ok(c)) {
+    l.cl_C = 8; l.cl_NC = l.nh;
+    const int64_t ks = l.H / 8 / 32, ksf = l.F / 8 / 32;                 // k32 tiles per rank: K = H phases, K = F phase
+    const int64_t nt[6] = {24, 8, 8, 8, l.F / l.nh / 8, 8};               // n-tiles per cluster (head: q|k|v = 192 features; 64; F/nh)
+    for (int i = 0; i < 6; i++) {
+      l.cp_slice[i] = nt[i] * (i == 5 ? ksf : ks) * 512;
+      l.cp[i] = take(l.cp_slice[i] * l.cl_NC * l.cl_C) - base;
+    }
+  }
   l.layer_stride = o - base;
   o = base + l.layer_stride * l.L;
   l.final_ln_w = take(l.H * 4); l.final_ln_b = take(l.H * 4);
@@ -108,6 +140,8 @@ struct WorkspaceLayout {
   int64_t ctrl, progress, gen, raw_ids, cur_ids, eos_seen, unfinished, first_unf, prompt_mask, enc_mask;
   int64_t x, qkv, attn, qc, hbuf, hidden, logits, scores, cross_tmp, cross_kv, self_kv;
   int64_t img_x, img_attn, img_h;  // fused step kernel: activations as tile images [chunk][32][H + 8] (step.cu stage_tile)
+  int64_t cl_x, cl_attn, cl_h;     // cluster step kernel: K-sliced images [8][32][K/8 + 8] (step2.cu)
+  int64_t row_stats;               // [max(B*(P+1), B*S)][2] f32: LayerNorm row statistics of the tcgen05 prefill GEMMs
   int64_t cross_layer_stride, self_layer_stride;  // bytes
   int64_t raw_ld;                                  // raw_ids leading dimension (elements)
   int64_t total;
@@ -141,6 +175,10 @@ static inline WorkspaceLayout make_workspace(const ptts_decoder_config& c, int B
   w.img_x = take((int64_t)32 * (l.H + 8) * 2);
   w.img_attn = take((int64_t)32 * (l.H + 8) * 2);
   w.img_h = take((int64_t)((l.F + l.H - 1) / l.H) * 32 * (l.H + 8) * 2);
+  w.row_stats = take((int64_t)(w.Mmax > rows_enc ? w.Mmax : rows_enc) * 2 * 4);
+  w.cl_x = take((int64_t)8 * 32 * (l.H / 8 + 8) * 2);
+  w.cl_attn = take((int64_t)8 * 32 * (l.H / 8 + 8) * 2);
+  w.cl_h = take((int64_t)8 * 32 * (l.F / 8 + 8) * 2);
   w.logits = take((int64_t)w.BK * l.V * 4);
   w.scores = take((int64_t)w.BK * l.V * 4);
   w.cross_layer_stride = align_up(rows_enc * l.ckv_rows * l.es, 256);

@@ -639,7 +639,7 @@ int launch_decode_step(const StepParams& p, int grid, cudaStream_t st) {
   static int attr_done[3] = {0, 0, 0};
   const int fi = p.sample_items <= 1 ? 0 : (p.sample_items <= 5 ? 1 : 2);
   if (!attr_done[fi]) {
-    PTTS_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PTTS_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));  // (+ 256 B of static shared memory: the sampler scratch)
     attr_done[fi] = 1;
   }
   PTTS_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(ST_THREADS), args, (size_t)smem, st));

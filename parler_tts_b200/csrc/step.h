@@ -35,9 +35,16 @@ struct StepParams {
   int dbg;                 // PTTS_DBG measurement switches, all off by default (1: no weight L2 prefetch, 2: no K/V prefetch,
                            // 4 / 8: omit the shared-memory proxy fence before the weight / tile copy -- timing experiments only)
   long long* prof;         // optional [(8L+3)][8] clock64 timestamps written by CTA 0 (debug / profiles)
+  // ---- cluster step kernel (step2.cu) ----
+  int64_t cp[6], cp_slice[6];   // per-layer offsets / slice bytes of the (phase, cluster, rank) weight slices (layout.h)
+  bf16 *cl_x, *cl_attn, *cl_h;  // K-sliced activation images [8][32][K/8 + 8]
 };
 
 int step_smem_bytes(const StepParams& p);
 int launch_decode_step(const StepParams& p, int grid, cudaStream_t st);
+// cluster step kernel (step2.cu)
+bool cluster_step_available(const StepParams& p);
+int launch_decode_step_cluster(const StepParams& p, cudaStream_t st);
+int cluster_pack_layer(const char* layer_src, char* layer_dst, const int64_t* mat_off, const int64_t* cp_off, int nh, int H, int F, cudaStream_t st);
 
 }  // namespace ptts

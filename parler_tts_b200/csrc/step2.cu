@@ -1,0 +1,697 @@
+// step2.cu -- the CLUSTER decode step: one persistent kernel per generated token, 6 device-wide phases per layer (bf16).
+//
+// Replaces the same reference code as step.cu (ParlerTTSForCausalLM.forward with q_len == 1, modeling_parler_tts.py:1865-1974 /
+// :983-1074, plus one iteration of GenerationMixin._sample) for the shapes layout.h::cluster_shape_ok() accepts (Parler-TTS-Mini:
+// MHA, one head per cluster).  step.cu's design -- 148 CTAs that each need the WHOLE 32 x H activation tile in every one of the
+// 8 dependent phases of a layer -- measured 6.5 us per phase: ~2 us device-wide barrier, 1.3 us to pull the 66 KB tile, 0.6 us of
+// LayerNorm statistics over it, an 8-warp split-K reduction through shared memory; 4.5 x the HBM time of the bytes it moves
+// (profiles/r01_step_phases.md, r02_step_phases.md).  This kernel cuts the dependent chain and the per-CTA fixed work:
+//
+//   * grid = 16 clusters x 8 CTAs (cudaLaunchAttributeClusterDimension).  Cluster c OWNS head c: its q/k/v features, its K/V
+//     cache items, its 64 out-proj / fc2 features and its F/16 fc1 features.  Rank r of a cluster reduces K-slice r (K/8 columns):
+//     a CTA stages 8.7 KB of activations per phase instead of 66 KB, every warp owns whole n-tiles (no split-K through shared
+//     memory), and the eight partial sums are exchanged through DISTRIBUTED SHARED MEMORY with one cp.async.bulk
+//     (shared::cta -> shared::cluster, mbarrier complete_tx) per peer.
+//   * the exchange of a projection that feeds attention is ROW-partitioned (rank r receives rows 4r..4r+3 of q|k|v for head c),
+//     so RoPE, the KV-cache append and the attention of those 4 (row, head) items run inside the same phase:
+//     QKV -> self-attention and q_cross -> cross-attention need no device-wide barrier between them.  6 barriers per layer, not 8.
+//   * the residual stream slice a CTA owns (32 rows x 8 features) never leaves its shared memory.
+//   * weights: one contiguous slice per (phase, cluster, rank) (layout.h cpack, built once by ptts_decoder_finalize), streamed by
+//     ONE bulk copy into a 2 x 64 KB ring two phases ahead and pulled HBM -> L2 a layer ahead (layer 0 of the NEXT token is
+//     prefetched during the lm-head phase: L2 survives the kernel boundary).
+//   * the activation slice of the next phase is requested by the barrier's polling thread the moment the barrier opens.
+// Reduction orders are fixed (k-tiles ascending inside a CTA, ranks 0..7 across the cluster): bit-reproducible run to run.  They
+// differ from step.cu / gemm.cu, so the two paths agree to bf16 accumulation-order noise, not bitwise (tests/test_gpu_parity.py).
+#include "attn_core.cuh"
+#include "common.cuh"
+#include "kernels.h"
+#include "ln_stats.cuh"
+#include "sample_core.cuh"
+#include "step.h"
+
+namespace ptts {
+namespace cl {
+
+constexpr int C = 8;            // CTAs per cluster == warps per CTA (warp w produces the block that rank w finalises)
+constexpr int THREADS = 256;
+constexpr int ROWS = 32;        // batch rows (two m16 tiles)
+constexpr int ATT_CH = 16;      // keys per K/V ring stage of an attention warp
+constexpr int HDR = 8192;       // mbarriers | row stats | stat partials | residual slice | folded-LN vectors
+constexpr int WB_BYTES = 65536; // one weight ring buffer
+constexpr int OFF_STATS = 256, OFF_PART = 512, OFF_RES = 2560, OFF_CVEC = 4096;
+constexpr int R_OFF = HDR + 2 * WB_BYTES;
+// R region: [activation slice | send blocks] (phase dependent split) then the receive slots; attention scratch and the lm-head
+// tile alias all of it.  Sized for Mini (H = 1024, F = 4096): fc1 exchange blocks of 256 B stats + 32 x 36 floats.
+constexpr int U_BYTES = 47616, RECV_BYTES = 38912, R_BYTES = U_BYTES + RECV_BYTES;
+constexpr int QKV_OFF = R_BYTES - 2048;   // [4 rows][192] bf16 q|k|v (or [4][64] q_cross) of this rank's attention items
+constexpr int SMEM_BYTES = R_OFF + R_BYTES;
+static_assert(SMEM_BYTES <= 227 * 1024, "cluster step kernel shared memory");
+
+// ---- PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int what) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 22)) { printf("ptts: cluster step mbarrier timeout (cta %d, barrier kind %d)\n", (int)blockIdx.x, what); __trap(); }
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(s32(dst_smem)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
+}
+// this CTA's shared memory -> a peer's shared memory (DSMEM), completion counted on the PEER's mbarrier
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster_addr, const void* src_smem, uint32_t bytes, uint32_t bar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster_addr), "r"(s32(src_smem)), "r"(bytes), "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r; }
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+  const char* c = reinterpret_cast<const char*>(p);
+  while (bytes > 0) {
+    const uint32_t n = bytes > 32768u ? 32768u : bytes;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(c), "r"(n) : "memory");
+    c += n;
+    bytes -= n;
+  }
+}
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) { unsigned v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const void* smem_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(s32(smem_ptr)));
+}
+__device__ __forceinline__ void prof_mark(long long* prof, int slot) { if (prof != nullptr && threadIdx.x == 0) prof[slot] = clock64(); }
+
+// ---- device-wide barrier (same protocol as step.cu) -----------------------------------------------
+// `post` runs on thread 0 the moment the barrier opens (before the CTA is released): the next phase's activation copy.
+// `side` runs on thread 32 while thread 0 polls.
+template <typename Post, typename Side>
+__device__ __forceinline__ unsigned grid_sync(unsigned* ctr, unsigned target, int ph, Post post, Side side) {
+  target += gridDim.x;
+  asm volatile("fence.proxy.async.global;" ::: "memory");  // this thread's global writes -> other CTAs' TMA reads (writer side)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    red_release_add(ctr, 1u);
+    unsigned spins = 0;
+    while (ld_relaxed(ctr) < target) {
+      if (++spins > (1u << 24)) { printf("ptts: cluster step grid barrier timeout (cta %d target %u seen %u phase %d)\n", (int)blockIdx.x, target, ld_relaxed(ctr), ph); __trap(); }
+    }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    post();
+  } else if (threadIdx.x == 32) {
+    side();
+  }
+  __syncthreads();
+  return target;
+}
+
+// phase kinds of a layer
+enum { PH_QKV = 0, PH_O = 1, PH_QC = 2, PH_OC = 3, PH_FC1 = 4, PH_FC2 = 5 };
+
+// source of weight job j for this CTA (jobs: 6 per layer in phase order, then this CTA's lm-head tasks)
+__device__ __forceinline__ bool weight_job(const StepParams& p, int j, int cta, const char*& src, uint32_t& bytes) {
+  const int nl = 6 * p.L;
+  if (j < nl) {
+    const int l = j / 6, ph = j - 6 * l;
+    bytes = (uint32_t)p.cp_slice[ph];
+    src = p.blob + p.layer0 + p.layer_stride * l + p.cp[ph] + (int64_t)cta * p.cp_slice[ph];
+    return true;
+  }
+  const int task = cta + (int)gridDim.x * (j - nl);
+  const int ntasks = p.K * p.V / 32;
+  if (task >= ntasks) return false;
+  bytes = (uint32_t)(4 * p.H * 16);  // 4 n-tiles x K (fragment order: 16 B per (n-tile, k-pair) lane row)
+  src = p.blob + p.heads + (int64_t)task * bytes;
+  return true;
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  Ctrl* ctrl = p.sa.ctrl;
+  if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(size_t)(6 * p.L + 2) * 8 + 3] = clock64();
+  if (ctrl->active == 0) return;  // generation finished: the rest of the enqueued steps are no-ops (uniform over the grid)
+  const int cur_len = ctrl->cur_len;
+  const unsigned gen = (unsigned)ctrl->launch_gen;
+  const int pos = p.P + cur_len - 1;  // cache position of the token being fed
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.H, F = p.F, B = p.B;
+  const int rank = (int)cluster_rank();
+  const int cta = (int)blockIdx.x;         // = cluster * 8 + rank
+  const int cluster = cta >> 3;            // == the attention head this cluster owns
+  const int Ks = H / C, KsF = F / C;       // K-slice widths
+  const int pitch = Ks + 8, pitchF = KsF + 8;
+  const int qe = F / p.nh / 64;            // fc1 n-tiles per rank (Mini: 4)
+
+  uint64_t* abar = reinterpret_cast<uint64_t*>(smem);        // activation slice
+  uint64_t* wbar = abar + 1;                                  // [2] weight ring
+  uint64_t* xbar = abar + 3;                                  // cluster exchange
+  uint64_t* attbars = reinterpret_cast<uint64_t*>(smem + 128);  // [8 warps][2] K/V rings
+  float* stats = reinterpret_cast<float*>(smem + OFF_STATS);   // [32][2] mean, rstd
+  float* part = reinterpret_cast<float*>(smem + OFF_PART);     // [8][32][2]
+  float* res_s = reinterpret_cast<float*>(smem + OFF_RES);     // [32][8] residual stream slice owned by this CTA
+  float* cvec = reinterpret_cast<float*>(smem + OFF_CVEC);     // c1[256] | c2[256] of the current phase's features
+  unsigned char* Rg = smem + R_OFF;
+  uint32_t par_a = 0, par_w = 0, par_x = 0, att_parity = 0;
+
+  if (tid == 0) {
+    mbar_init(abar, 1); mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1); mbar_init(xbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  attention_decode_init_warp(attbars + 2 * warp, lane);
+  cluster_arrive(); cluster_wait();   // every peer's mbarriers exist before any remote complete_tx
+  cluster_arrive();                   // pre-arm: pairs with the first phase's "exchange buffers free" wait
+  unsigned* const bar_ctr = p.bar + (gen & 1u);
+  unsigned bar_target = 0u;
+  if (cta == 0 && tid == 0) p.bar[(gen + 1u) & 1u] = 0u;  // the counter the NEXT launch will use
+
+  const char* blob = p.blob;
+  long long* const prof0 = (p.prof != nullptr && cta == 0) ? p.prof : nullptr;
+  long long* prof = prof0;
+  prof_mark(prof, 0);
+
+  // weight ring: job j lives in buffer j & 1; jobs 0 and 1 are requested now, job j + 2 when job j's MMA loop has retired
+  auto issue_weight_job = [&](int j) {  // ONE thread
+    const char* src; uint32_t bytes;
+    if (!weight_job(p, j, cta, src, bytes)) return;
+    fence_proxy_async_smem();
+    mbar_expect_tx(&wbar[j & 1], bytes);
+    bulk_g2s(smem + HDR + (j & 1) * WB_BYTES, src, bytes, &wbar[j & 1]);
+  };
+  auto prefetch_weight_job = [&](int j) {  // ONE thread: HBM -> L2, a layer ahead
+    const char* src; uint32_t bytes;
+    if (weight_job(p, j, cta, src, bytes)) l2_prefetch(src, bytes);
+  };
+  // K/V rows of this rank's 4 attention items (rows 4 rank .. 4 rank + 3, head = cluster) -> L2
+  auto prefetch_kv = [&](int l, bool cross) {  // ONE thread
+    const int T = cross ? p.S : p.Tmax, n = cross ? p.S : pos;
+    if (n <= 0) return;
+    const char* kc = cross ? p.cross_kv + p.cross_layer_stride * l : p.self_kv + p.self_layer_stride * l;
+    const size_t vofs = (size_t)B * p.nh * T * HD * 2;
+    for (int i = 0; i < 4; i++) {
+      const int b = 4 * rank + i;
+      if (b >= B) break;
+      const char* k = kc + ((size_t)b * p.nh + cluster) * T * HD * 2;
+      l2_prefetch(k, (uint32_t)(n * HD * 2));
+      l2_prefetch(k + vofs, (uint32_t)(n * HD * 2));
+    }
+  };
+  if (tid == 0) { issue_weight_job(0); issue_weight_job(1); }
+  if (tid == 64) { for (int j = 2; j < 6; j++) prefetch_weight_job(j); prefetch_kv(0, false); prefetch_kv(0, true); }
+
+  // global activation images, K-sliced for their consumer: [8 slices][32 rows][slice width + 8] bf16
+  bf16* const x_img = p.cl_x;       // slices of H/8 columns (consumers: QKV, q_cross, fc1, lm heads)
+  bf16* const a_img = p.cl_attn;    // slices of H/8 columns = 2 heads (consumers: out_proj, cross out_proj)
+  bf16* const h_img = p.cl_h;       // slices of F/8 columns (consumer: fc2)
+  const int x_slice_elems = ROWS * pitch, h_slice_elems = ROWS * pitchF;
+  // where this CTA's 8 residual / out-proj features live in the x image: feature n = cluster * 64 + rank * 8 + f
+  const int xo_slice = (cluster * 64 + rank * 8) / Ks, xo_col = (cluster * 64 + rank * 8) % Ks;
+
+  // ---- embeddings: this CTA's 32 x 8 slice of sum_k embed_k[id] (+ position) -> residual slice + x image -----------------
+  {
+    const bf16* tables = reinterpret_cast<const bf16*>(blob + p.embed);
+    const bf16* postab = p.rope ? nullptr : reinterpret_cast<const bf16*>(blob + p.pos);
+    const int row = tid >> 3, f = tid & 7, n = cluster * 64 + rank * 8 + f;
+    float v = 0.f;
+    if (row < B) {
+      float ev[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+        if (k < p.K) ev[k] = __bfloat162float(tables[((size_t)k * (p.V + 1) + p.sa.cur_ids[row * p.K + k]) * H + n]);
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+        if (k < p.K) v = (k == 0) ? ev[k] : DT<bf16>::rnd(v + ev[k]);
+      if (postab != nullptr) v = DT<bf16>::rnd(v + __bfloat162float(postab[(size_t)pos * H + n]));
+    }
+    res_s[row * 8 + f] = v;
+    x_img[(size_t)xo_slice * x_slice_elems + row * pitch + xo_col + f] = __float2bfloat16_rn(v);
+  }
+  prof_mark(prof, 6);
+  // the first phase's activation slice is requested by the polling thread as soon as the barrier opens
+  auto request_slice = [&](const bf16* img_slice, uint32_t bytes) {  // thread 0
+    fence_proxy_async_smem();
+    mbar_expect_tx(abar, bytes);
+    bulk_g2s(Rg, img_slice, bytes, abar);
+  };
+  bar_target = grid_sync(bar_ctr, bar_target, -1,
+                         [&]() { request_slice(x_img + (size_t)rank * x_slice_elems, (uint32_t)(x_slice_elems * 2)); }, []() {});
+  prof_mark(prof, 7);
+
+  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol = (lane >> 4) * 8;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int n_phases = 6 * p.L;
+
+#pragma unroll 1
+  for (int ph = 0; ph < n_phases; ph++) {
+    const int l = ph / 6, sub = ph - 6 * l;
+    prof = prof0 ? prof0 + (size_t)(ph + 1) * 8 : nullptr;
+    prof_mark(prof, 0);
+    const char* lb = blob + p.layer0 + p.layer_stride * l;
+    const bool rowpart = (sub == PH_QKV || sub == PH_QC);
+    const bool has_ln = (sub == PH_QKV || sub == PH_QC || sub == PH_FC1);
+    const int q = (sub == PH_QKV) ? 3 : (sub == PH_FC1 ? qe : 1);   // n-tiles per warp
+    const int Nc = C * q * 8;                                        // features of this cluster in this phase
+    const int KT = (sub == PH_FC2 ? KsF : Ks) >> 5;                  // k32 tiles of this rank's slice
+    const int apitch = (sub == PH_FC2) ? pitchF : pitch;
+    const int act_bytes = ROWS * apitch * 2;
+    // exchange geometry
+    const int RS = (q == 1) ? 8 : 8 * q + 4;                         // floats per row of a feature-partitioned block
+    const int blk = rowpart ? (32 + 4 * Nc * 4) : (256 + ROWS * RS * 4);
+    unsigned char* send = Rg + ((act_bytes + 127) & ~127);
+    unsigned char* recv = Rg + U_BYTES;
+
+    // folded-LayerNorm vectors of this phase's features (read after two CTA barriers)
+    if (has_ln) {
+      const float* c1; int ntot;
+      if (sub == PH_QKV) { c1 = reinterpret_cast<const float*>(lb + p.c_qkv); ntot = p.qkv_rows; }
+      else if (sub == PH_QC) { c1 = reinterpret_cast<const float*>(lb + p.c_qc); ntot = H; }
+      else { c1 = reinterpret_cast<const float*>(lb + p.c_fc1); ntot = F; }
+      const int nown = rowpart ? Nc : 8 * q;
+      if (tid < nown) {
+        int n;
+        if (sub == PH_QKV) n = (tid >> 6) * (p.nh * HD) + cluster * HD + (tid & 63);
+        else if (sub == PH_QC) n = cluster * HD + tid;
+        else n = cluster * (F / p.nh) + rank * 8 * q + tid;
+        cvec[tid] = c1[n];
+        cvec[256 + tid] = c1[ntot + n];
+      }
+    }
+
+    // ---- MMA: this warp's q n-tiles over the rank's K slice ----
+    mbar_wait(&wbar[ph & 1], (par_w >> (ph & 1)) & 1u, 1);
+    par_w ^= 1u << (ph & 1);
+    mbar_wait(abar, par_a, 0);
+    par_a ^= 1u;
+    prof_mark(prof, 1);
+    float acc[2][4][4];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) acc[a][j][e] = 0.f;
+    RowStatFrag rst;
+    row_stat_zero(rst);
+    {
+      const bf16* xs = reinterpret_cast<const bf16*>(Rg);
+      const uint4* wb = reinterpret_cast<const uint4*>(smem + HDR + (ph & 1) * WB_BYTES) + (size_t)(warp * q) * KT * 32 + lane;
+      for (int kt = 0; kt < KT; kt++) {
+        uint32_t a[2][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) ldsm4(a[mt][j], xs + (size_t)(mt * 16 + lrow) * apitch + kt * 32 + j * 16 + lcol);
+        if (has_ln && (kt & 7) == warp) {  // row statistics of k-tile kt ride on the fragments already loaded
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++) { row_stat_mma(rst, mt, a[mt][0]); row_stat_mma(rst, mt, a[mt][1]); }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (j < q) {
+            const uint4 w = wb[((size_t)j * KT + kt) * 32];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+              mma_bf16_16816(acc[mt][j], a[mt][0], w.x, w.y);
+              mma_bf16_16816(acc[mt][j], a[mt][1], w.z, w.w);
+            }
+          }
+        }
+      }
+    }
+    prof_mark(prof, 2);
+    __syncthreads();  // activation slice and weight buffer are dead
+    if (tid == 32) {  // refill the ring two jobs ahead; pull the same phase of the next layer (or the lm heads) into L2
+      issue_weight_job(ph + 2);
+      prefetch_weight_job(ph + 6);
+      if (sub == PH_O && l + 1 < p.L) prefetch_kv(l + 1, false);
+      if (sub == PH_OC && l + 1 < p.L) prefetch_kv(l + 1, true);
+    }
+    cluster_wait();  // every peer is past its previous exchange: my send blocks have been read, its receive slots are free
+
+    // ---- partial sums -> send blocks ----
+    if (has_ln) row_stat_store(rst, part, warp, lane);
+    if (!rowpart) {   // block w = [stats 32x2][32 rows][RS]: everything rank w finalises
+      float* blkp = reinterpret_cast<float*>(send + (size_t)warp * blk + 256);
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (j < q) {
+            float* base = blkp + (size_t)(mt * 16 + g) * RS + j * 8 + 2 * t4;
+            *reinterpret_cast<float2*>(base) = make_float2(acc[mt][j][0], acc[mt][j][1]);
+            *reinterpret_cast<float2*>(base + 8 * RS) = make_float2(acc[mt][j][2], acc[mt][j][3]);
+          }
+        }
+    } else {          // block d = [stats 4x2][4 rows][Nc]: rows 4d..4d+3, all of the head's features
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (j < q) {
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+              const int row = mt * 16 + g + 8 * hh, col = (warp * q + j) * 8 + 2 * t4;
+              float* dst = reinterpret_cast<float*>(send + (size_t)(row >> 2) * blk + 32) + (row & 3) * Nc + col;
+              *reinterpret_cast<float2*>(dst) = make_float2(acc[mt][j][2 * hh], acc[mt][j][2 * hh + 1]);
+            }
+          }
+        }
+    }
+    __syncthreads();
+    if (has_ln && tid < ROWS) {  // this CTA's partial (S1, S2) of row tid over its K slice -> into every block that needs it
+      float S1 = 0.f, S2 = 0.f;
+      const int nw = KT < 8 ? KT : 8;
+      for (int w = 0; w < nw; w++) { S1 += part[((size_t)w * 32 + tid) * 2]; S2 += part[((size_t)w * 32 + tid) * 2 + 1]; }
+      if (!rowpart) {
+#pragma unroll
+        for (int d = 0; d < C; d++) *reinterpret_cast<float2*>(send + (size_t)d * blk + tid * 8) = make_float2(S1, S2);
+      } else {
+        *reinterpret_cast<float2*>(send + (size_t)(tid >> 2) * blk + (tid & 3) * 8) = make_float2(S1, S2);
+      }
+    }
+    __syncthreads();
+    if (tid < C && tid != rank) {  // one DSMEM bulk copy per peer: my block for rank `tid` -> its receive slot [my rank]
+      fence_proxy_async_smem();
+      bulk_s2peer(mapa(s32(recv + (size_t)rank * blk), (uint32_t)tid), send + (size_t)tid * blk, (uint32_t)blk, mapa(s32(xbar), (uint32_t)tid));
+    }
+    if (tid == C) mbar_expect_tx(xbar, (uint32_t)((C - 1) * blk));
+    mbar_wait(xbar, par_x, 2);
+    par_x ^= 1u;
+    prof_mark(prof, 3);
+
+    // ---- epilogue: sum the 8 partial blocks in rank order, LayerNorm fix-up, activation / residual ----
+    auto block_of = [&](int src) -> const unsigned char* { return (src == rank) ? send + (size_t)rank * blk : recv + (size_t)src * blk; };
+    if (!rowpart) {
+      if (has_ln && tid < ROWS) {
+        float S1 = 0.f, S2 = 0.f;
+        for (int s = 0; s < C; s++) { const float2 v = *reinterpret_cast<const float2*>(block_of(s) + tid * 8); S1 += v.x; S2 += v.y; }
+        const float mean = S1 / (float)H;
+        stats[2 * tid] = mean;
+        stats[2 * tid + 1] = rsqrtf(fmaxf(S2 / (float)H - mean * mean, 0.f) + p.eps);
+      }
+      if (has_ln) __syncthreads();
+      const int row = tid >> 3, f0 = tid & 7;
+      if (row < B) {
+        for (int i = 0; i < q; i++) {
+          const int f = f0 + 8 * i;
+          float v = 0.f;
+#pragma unroll
+          for (int s = 0; s < C; s++) v += reinterpret_cast<const float*>(block_of(s) + 256)[row * RS + f];
+          if (sub == PH_FC1) {
+            v = stats[2 * row + 1] * (v - stats[2 * row] * cvec[f]) + cvec[256 + f];
+            v = apply_act(DT<bf16>::rnd(v), p.act);
+            const int n = cluster * (F / p.nh) + rank * 8 * q + f;   // h feature -> slice n / KsF of the fc2 image
+            h_img[(size_t)(n / KsF) * h_slice_elems + row * pitchF + (n % KsF)] = __float2bfloat16_rn(v);
+          } else {  // out-proj / cross out-proj / fc2: residual add on the slice this CTA owns
+            v = DT<bf16>::rnd(res_s[row * 8 + f] + DT<bf16>::rnd(v));
+            res_s[row * 8 + f] = v;
+            x_img[(size_t)xo_slice * x_slice_elems + row * pitch + xo_col + f] = __float2bfloat16_rn(v);
+          }
+        }
+      }
+    } else {
+      if (tid < 4) {  // rows 4 rank + tid
+        float S1 = 0.f, S2 = 0.f;
+        for (int s = 0; s < C; s++) { const float2 v = *reinterpret_cast<const float2*>(block_of(s) + tid * 8); S1 += v.x; S2 += v.y; }
+        const float mean = S1 / (float)H;
+        stats[2 * tid] = mean;
+        stats[2 * tid + 1] = rsqrtf(fmaxf(S2 / (float)H - mean * mean, 0.f) + p.eps);
+      }
+      __syncthreads();
+      bf16* qkv_s = reinterpret_cast<bf16*>(Rg + QKV_OFF);  // [4][Nc]
+      for (int idx = tid; idx < 4 * Nc; idx += THREADS) {
+        const int r4 = idx / Nc, col = idx - r4 * Nc;
+        float v = 0.f;
+#pragma unroll
+        for (int s = 0; s < C; s++) v += reinterpret_cast<const float*>(block_of(s) + 32)[r4 * Nc + col];
+        v = stats[2 * r4 + 1] * (v - stats[2 * r4] * cvec[col]) + cvec[256 + col];
+        qkv_s[idx] = __float2bfloat16_rn(v);
+      }
+    }
+    prof_mark(prof, 4);
+    __syncthreads();   // receive slots and this CTA's reads of its own send block are done (and q|k|v complete)
+    cluster_arrive();
+    if (rowpart) {
+      // attention scratch aliases the send blocks: the peers must have RECEIVED them (each is past its exchange wait) first
+      cluster_wait();
+      cluster_arrive();  // re-arm for the next phase's "exchange buffers free" wait
+    }
+
+    // ---- attention of this rank's 4 (row, head) items: two warps per item ----
+    if (rowpart) {
+      AttnArgs a{};
+      a.ctrl = nullptr; a.B = B; a.nh = p.nh; a.nkv = p.nh; a.q_len = 1;
+      a.past_from_ctrl = 0; a.past_len = pos; a.prefix = p.P;
+      a.rope = p.rope; a.rope_cos = blob + p.rope_cos; a.rope_sin = blob + p.rope_sin; a.scale = p.scale;
+      const bf16* qkv_s = reinterpret_cast<const bf16*>(Rg + QKV_OFF);
+      // row b = 4 rank + i, head = cluster: q at qkv_s[i][0..63] (k at +64, v at +128 for the self phase)
+      const bf16* qbase = qkv_s - (size_t)(4 * rank) * Nc - (size_t)cluster * HD;
+      a.q = qbase; a.ldq = Nc; a.q_col0 = 0;
+      // attn image: row b, head h -> slice h / 2, column (h % 2) * 64
+      a.ldo = pitch;
+      a.out = a_img + (size_t)(cluster >> 1) * x_slice_elems + (cluster & 1) * HD - (size_t)cluster * HD;
+      if (sub == PH_QKV) {
+        a.knew = qbase; a.vnew = qbase; a.ldkv = Nc; a.k_col0 = HD; a.v_col0 = 2 * HD;
+        char* kc = p.self_kv + p.self_layer_stride * l;
+        a.kcache = kc; a.vcache = kc + (size_t)B * p.nh * p.Tmax * HD * 2;
+        a.kv_b_stride = (int64_t)p.nh * p.Tmax * HD; a.kv_h_stride = (int64_t)p.Tmax * HD; a.kv_t_stride = HD;
+        a.key_mask = p.prompt_mask; a.mask_len = p.P; a.mask_ld = p.P;
+        a.cross = 0; a.kv_len = 0; a.kv_capacity = p.Tmax;
+      } else {
+        a.knew = nullptr; a.vnew = nullptr;
+        char* ck = p.cross_kv + p.cross_layer_stride * l;
+        a.kcache = ck; a.vcache = ck + (size_t)B * p.nh * p.S * HD * 2;
+        a.kv_b_stride = (int64_t)p.nh * p.S * HD; a.kv_h_stride = (int64_t)p.S * HD; a.kv_t_stride = HD;
+        a.key_mask = p.enc_mask; a.mask_len = p.S; a.mask_ld = p.S;
+        a.cross = 1; a.kv_len = p.S; a.kv_capacity = p.S;
+      }
+      const int pair = warp >> 1, part_i = warp & 1;
+      const int b = 4 * rank + pair;
+      unsigned char* region = Rg + (size_t)warp * attn_decode_smem_per_warp<bf16, ATT_CH>();
+      float* xch = reinterpret_cast<float*>(Rg + (size_t)C * attn_decode_smem_per_warp<bf16, ATT_CH>()) + pair * 128;
+      if (b < B) attention_decode_item_warp<bf16, ATT_CH>(a, b, cluster, pos, region, attbars + 2 * warp, lane, att_parity, part_i, 2, xch, pair + 1);
+      prof_mark(prof, 5);
+    }
+    prof_mark(prof, 6);
+
+    // ---- device-wide barrier; the next phase's activation slice is requested the moment it opens ----
+    const int nsub = (sub + 1) % 6;
+    const bool last = (ph + 1 == n_phases);
+    const bf16* nimg; uint32_t nbytes;
+    if (last) { nimg = x_img; nbytes = (uint32_t)(C * x_slice_elems * 2); }                       // lm heads: the whole x image
+    else if (nsub == PH_O || nsub == PH_OC) { nimg = a_img + (size_t)rank * x_slice_elems; nbytes = (uint32_t)(x_slice_elems * 2); }
+    else if (nsub == PH_FC2) { nimg = h_img + (size_t)rank * h_slice_elems; nbytes = (uint32_t)(h_slice_elems * 2); }
+    else { nimg = x_img + (size_t)rank * x_slice_elems; nbytes = (uint32_t)(x_slice_elems * 2); }
+    bar_target = grid_sync(bar_ctr, bar_target, ph, [&]() { request_slice(nimg, nbytes); }, []() {});
+    prof_mark(prof, 7);
+  }
+  cluster_wait();  // balance the last phase's arrive
+
+  // ---- final LayerNorm + K lm heads: N-split over all CTAs (4 n-tiles per task, full K), no exchange ----
+  prof = prof0 ? prof0 + (size_t)(n_phases + 1) * 8 : nullptr;
+  prof_mark(prof, 0);
+  {
+    const int ntasks = p.K * p.V / 32;
+    const float* c1 = reinterpret_cast<const float*>(blob + p.c_heads);
+    const float* c2 = c1 + p.K * p.V;
+    if (tid == 64) {  // layer 0 of the NEXT token -> L2 (the cache outlives the kernel): its first phases start warm
+      for (int j = 0; j < 6; j++) prefetch_weight_job(j);
+    }
+    mbar_wait(abar, par_a, 3);
+    par_a ^= 1u;
+    const bf16* xs = reinterpret_cast<const bf16*>(Rg);   // [8 slices][32][pitch]
+    const int KTH = H >> 5;                                // k32 tiles of the full row
+    {  // row statistics over the full rows: k-tile kt by warp kt % 8
+      RowStatFrag rst;
+      row_stat_zero(rst);
+      for (int kt = warp; kt < KTH; kt += 8) {
+        const bf16* sl = xs + (size_t)(kt / (Ks >> 5)) * x_slice_elems + (kt % (Ks >> 5)) * 32;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            uint32_t a[4];
+            ldsm4(a, sl + (size_t)(mt * 16 + lrow) * pitch + j * 16 + lcol);
+            row_stat_mma(rst, mt, a);
+          }
+      }
+      row_stat_store(rst, part, warp, lane);
+      __syncthreads();
+      row_stat_finalize(part, H, ROWS, p.eps, stats);
+      __syncthreads();
+    }
+    prof_mark(prof, 1);
+    float* red = reinterpret_cast<float*>(Rg + (size_t)C * x_slice_elems * 2);  // [4 n-tiles][32][8] partials of the upper K half
+    const int jn = warp >> 1, kh = warp & 1;   // this warp: n-tile jn of the task, K half kh
+    int job = n_phases;
+    for (int task = cta; task < ntasks; task += (int)gridDim.x, job++) {
+      mbar_wait(&wbar[job & 1], (par_w >> (job & 1)) & 1u, 4);
+      par_w ^= 1u << (job & 1);
+      float acc[2][4];
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) acc[a][e] = 0.f;
+      const uint4* wb = reinterpret_cast<const uint4*>(smem + HDR + (job & 1) * WB_BYTES) + (size_t)jn * KTH * 32 + lane;
+      for (int kt = kh * (KTH / 2); kt < (kh + 1) * (KTH / 2); kt++) {
+        const bf16* sl = xs + (size_t)(kt / (Ks >> 5)) * x_slice_elems + (kt % (Ks >> 5)) * 32;
+        const uint4 w = wb[(size_t)kt * 32];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          uint32_t a0[4], a1[4];
+          ldsm4(a0, sl + (size_t)(mt * 16 + lrow) * pitch + lcol);
+          ldsm4(a1, sl + (size_t)(mt * 16 + lrow) * pitch + 16 + lcol);
+          mma_bf16_16816(acc[mt], a0, w.x, w.y);
+          mma_bf16_16816(acc[mt], a1, w.z, w.w);
+        }
+      }
+      if (kh == 1) {
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+          float* base = red + ((size_t)jn * 32 + mt * 16 + g) * 8 + 2 * t4;
+          *reinterpret_cast<float2*>(base) = make_float2(acc[mt][0], acc[mt][1]);
+          *reinterpret_cast<float2*>(base + 64) = make_float2(acc[mt][2], acc[mt][3]);
+        }
+      }
+      __syncthreads();  // weight buffer dead, upper-half partials visible
+      if (tid == 32) issue_weight_job(job + 2);
+      if (kh == 0) {
+        const int n0 = task * 32 + jn * 8 + 2 * t4;
+        const float2 c1v = *reinterpret_cast<const float2*>(c1 + n0), c2v = *reinterpret_cast<const float2*>(c2 + n0);
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {
+            const int row = mt * 16 + g + 8 * hh;
+            if (row < B) {
+              const float2 up = *reinterpret_cast<const float2*>(red + ((size_t)jn * 32 + row) * 8 + 2 * t4);
+              const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+              const float v0 = DT<bf16>::rnd(rstd * (acc[mt][2 * hh] + up.x - mean * c1v.x) + c2v.x);
+              const float v1 = DT<bf16>::rnd(rstd * (acc[mt][2 * hh + 1] + up.y - mean * c1v.y) + c2v.y);
+              *reinterpret_cast<float2*>(p.logits + (size_t)row * p.K * p.V + n0) = make_float2(v0, v1);
+            }
+          }
+      }
+      __syncthreads();  // `red` is reused by the next task
+    }
+  }
+  prof_mark(prof, 6);
+  bar_target = grid_sync(bar_ctr, bar_target, n_phases, []() {}, []() {});
+  prof = prof0 ? prof0 + (size_t)(n_phases + 2) * 8 : nullptr;  // tail row: sampling / barrier
+  prof_mark(prof, 0);
+  if (p.do_sample_phase) {
+    const ptts_gen_params gp = *p.sa.gen;
+    const int BK = B * p.K;
+    for (int row = cta; row < BK; row += (int)gridDim.x) sample_row_cta<ITEMS>(p.sa, gp, nullptr, row, cur_len);
+    prof_mark(prof, 1);
+    bar_target = grid_sync(bar_ctr, bar_target, n_phases + 1, []() {}, []() {});
+    prof_mark(prof, 2);
+  }
+  if (cta == 0 && tid == 0) {
+    if (p.do_sample_phase) {
+      const int n = atomicAdd(&ctrl->n_unfinished, 0);
+      ctrl->cur_len = cur_len + 1;
+      ctrl->active = (n > 0) ? 1 : 0;
+      ctrl->steps_run += 1;
+      ctrl->n_unfinished = 0;
+    }
+    ctrl->launch_gen = (int)(gen + 1u);
+  }
+}
+
+// ---- weight repack: fragment-order matrices -> one contiguous slice per (phase, cluster, rank) --------------------------
+// Both layouts are made of the same 512-byte (n8 x k32) tiles, so the repack is a tile gather.
+__global__ void cluster_pack_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int ph, int nh, int ntc, int kts, int KT_src) {
+  // dst tile index = ((cta * ntc + j) * kts + ktl);  cta = cluster * 8 + rank
+  const int64_t tile = blockIdx.x;
+  const int ktl = (int)(tile % kts);
+  const int j = (int)((tile / kts) % ntc);
+  const int cta = (int)(tile / ((int64_t)kts * ntc));
+  const int cluster = cta >> 3, rank = cta & 7;
+  int n_tile;
+  if (ph == PH_QKV) n_tile = (j >> 3) * (nh * 8) + cluster * 8 + (j & 7);   // q | k | v rows of head `cluster` in the fused matrix
+  else n_tile = cluster * ntc + j;
+  const int kt = rank * kts + ktl;
+  dst[tile * 32 + threadIdx.x] = src[((int64_t)n_tile * KT_src + kt) * 32 + threadIdx.x];
+}
+
+}  // namespace cl
+
+// ---- host side ----------------------------------------------------------------------------------
+int cluster_pack_layer(const char* layer_src, char* layer_dst, const int64_t* mat_off, const int64_t* cp_off, int nh, int H, int F, cudaStream_t st) {
+  // mat_off: byte offsets (inside the layer) of wqkv, wo, wqc, woc, fc1, fc2; cp_off: of the six packed regions
+  const int ks = H / 8 / 32, ksf = F / 8 / 32;
+  const int ntc[6] = {24, 8, 8, 8, F / nh / 8, 8};
+  for (int ph = 0; ph < 6; ph++) {
+    const int kts = (ph == 5) ? ksf : ks;
+    const int KT_src = (ph == 5) ? F / 32 : H / 32;
+    const int64_t tiles = (int64_t)nh * 8 * ntc[ph] * kts;
+    cl::cluster_pack_kernel<<<(unsigned)tiles, 32, 0, st>>>(reinterpret_cast<const uint4*>(layer_src + mat_off[ph]),
+                                                            reinterpret_cast<uint4*>(layer_dst + cp_off[ph]), ph, nh, ntc[ph], kts, KT_src);
+  }
+  PTTS_LAUNCH_CHECK();
+  return PTTS_OK;
+}
+
+static const void* cluster_kernel_fn(const StepParams& p) {
+  if (p.sample_items <= 1) return (const void*)cl::decode_step_cluster_kernel<1>;
+  if (p.sample_items <= 5) return (const void*)cl::decode_step_cluster_kernel<5>;
+  return (const void*)cl::decode_step_cluster_kernel<9>;
+}
+
+static void cluster_launch_config(const StepParams& p, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, cudaStream_t st) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3((unsigned)(p.nh * cl::C));
+  cfg.blockDim = dim3(cl::THREADS);
+  cfg.dynamicSmemBytes = cl::SMEM_BYTES;
+  cfg.stream = st;
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cl::C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;   // every CTA spins on the others: co-residency must be guaranteed
+  at[1].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+}
+
+// true when the 16 x 8 cluster grid can be co-resident on this device
+bool cluster_step_available(const StepParams& p) {
+  const void* fn = cluster_kernel_fn(p);
+  static bool told = false;
+  auto why = [&](const char* what, cudaError_t e, int n) {
+    if (!told) fprintf(stderr, "ptts_b200: cluster step kernel not used (%s: %s, %d co-resident clusters of %d, need %d); the 148-CTA step kernel runs instead\n",
+                       what, cudaGetErrorString(e), n, cl::C, p.nh);
+    told = true;
+    cudaGetLastError();
+    return false;
+  };
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cl::SMEM_BYTES);
+  if (e != cudaSuccess) return why("shared memory attribute", e, 0);
+  cudaLaunchConfig_t cfg; cudaLaunchAttribute at[2];
+  cluster_launch_config(p, cfg, at, nullptr);
+  cfg.numAttrs = 1;  // the occupancy query takes the cluster shape
+  int n = 0;
+  e = cudaOccupancyMaxActiveClusters(&n, fn, &cfg);
+  if (e != cudaSuccess) return why("cluster occupancy query", e, n);
+  if (n < p.nh) return why("too few co-resident clusters", cudaSuccess, n);
+  return true;
+}
+
+int launch_decode_step_cluster(const StepParams& p, cudaStream_t st) {
+  const void* fn = cluster_kernel_fn(p);
+  cudaLaunchConfig_t cfg; cudaLaunchAttribute at[2];
+  cluster_launch_config(p, cfg, at, st);
+  void* args[] = {(void*)&p};
+  PTTS_CHECK_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+  return PTTS_OK;
+}
+
+}  // namespace ptts

@@ -258,7 +258,8 @@ class GenSession:
 
     @property
     def fused(self) -> int:
-        """0: decode steps use the multi-kernel path; 1: the fused persistent step kernel (one launch per token)."""
+        """0: decode steps use the multi-kernel path; 1: the fused persistent step kernel (one launch per token, step.cu);
+        2: its cluster variant (step2.cu: one cluster per head, 6 device-wide phases per layer)."""
         n = C.c_int32()
         _lib.check(_lib.lib().ptts_session_fused(self.h, C.byref(n)))
         return n.value
@@ -317,6 +318,22 @@ class GenerateOutput(dict):
         self[k] = v
 
 
+class ParlerTTSCache:
+    """`past_key_values` of ParlerTTSForCausalLM.forward: the device session that owns the pre-allocated self-attention K/V
+    cache (append in place at cache_position) and the cross-attention K/V projected once at the first call -- the roles of
+    EncoderDecoderCache(StaticCache, StaticCache) in the reference (:3254-3309)."""
+
+    def __init__(self, session: "GenSession"):
+        self.session = session
+        self.steps = 0
+
+    def get_seq_length(self) -> int:
+        return self.session.P + 1 + self.steps
+
+    def get_max_cache_shape(self) -> int:
+        return self.session.max_cache_len
+
+
 class ParlerTTSForCausalLM:
     """Decoder + K LM heads as a step operator over a KV-cached session (reference :1824-1974)."""
 
@@ -333,6 +350,53 @@ class ParlerTTSForCausalLM:
 
     def build_delay_pattern_mask(self, input_ids, bos_token_id, pad_token_id, max_length):
         return build_delay_pattern_mask(input_ids, bos_token_id, pad_token_id, max_length, self.num_codebooks)
+
+    @torch.no_grad()
+    def forward(self, input_ids: torch.LongTensor = None, attention_mask=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, prompt_hidden_states=None, prompt_attention_mask=None, past_key_values=None,
+                use_cache: bool = True, cache_position=None, return_dict: bool = True, max_cache_len: Optional[int] = None, **kwargs):
+        """The step operator an HF-style loop calls (reference :1865-1974): input_ids [B*K, 1] (delay mask already applied, as
+        prepare_inputs_for_generation does at :2909) -> logits [B*K, 1, V], over a KV cache kept in `past_key_values`.
+
+        * first call (past_key_values None): `encoder_hidden_states` [B, S, H] (already multiplied by their mask) and optionally
+          `prompt_hidden_states` [B, P, H] are required; the prompt prefix + the given ids go through ptts_prefill and a
+          ParlerTTSCache (the session: pre-allocated self- and cross-attention K/V) is returned as `past_key_values`.
+          Only the LAST position's logits are materialised (what `_sample` reads): shape [B*K, 1, V], not [B*K, P+1, V].
+        * later calls: the ids are appended (ptts_sample with forced tokens) and one cached step runs on the fused kernel
+          (ptts_decode_forward).
+        Inputs longer than one column, `inputs_embeds`, `labels` and `use_cache=False` belong to training / the no-cache path and
+        are outside this operator (ValueError)."""
+        if kwargs.get("inputs_embeds") is not None or kwargs.get("labels") is not None or not use_cache:
+            raise ValueError("ParlerTTSForCausalLM.forward on the B200 path is the cached decode-step operator: input_ids [B*K, 1], use_cache=True")
+        if input_ids is None or input_ids.dim() != 2 or input_ids.shape[1] != 1 or input_ids.shape[0] % self.num_codebooks != 0:
+            raise ValueError(f"input_ids must be [batch * num_codebooks, 1], got {None if input_ids is None else tuple(input_ids.shape)}")
+        B = input_ids.shape[0] // self.num_codebooks
+        ids = input_ids[:, 0].to(self.device, torch.int64).contiguous()
+        if past_key_values is None:
+            if encoder_hidden_states is None:
+                raise ValueError("the first call needs `encoder_hidden_states`")
+            S = encoder_hidden_states.shape[1]
+            P = 0 if prompt_hidden_states is None else prompt_hidden_states.shape[1]
+            cap = int(max_cache_len or self.config.max_position_embeddings)
+            sess = GenSession(self.engine, B, P, S, cap)   # an independent cache, not the engine's shared generate() session
+            sess.begin(cap - P, do_sample=False)
+            if not bool((ids == self.config.bos_token_id).all()):
+                raise ValueError("the first call must feed the decoder start (BOS) column")
+            sess.prefill(prompt_hidden_states, prompt_attention_mask if P > 0 else None, encoder_hidden_states, encoder_attention_mask)
+            past_key_values = ParlerTTSCache(sess)
+        else:
+            if not isinstance(past_key_values, ParlerTTSCache) or past_key_values.session.B != B:
+                raise ValueError("past_key_values must be the ParlerTTSCache returned by the first call (same batch)")
+            sess = past_key_values.session
+            sess.sample(forced=ids)
+            sess.decode_forward()
+            past_key_values.steps += 1
+        logits = sess.logits.clone().unsqueeze(1)   # [B*K, 1, V] fp32
+        if not return_dict:
+            return (logits, past_key_values)
+        return GenerateOutput(logits=logits, past_key_values=past_key_values)
+
+    __call__ = forward
 
     @staticmethod
     def apply_delay_pattern_mask(input_ids, decoder_pad_token_mask):
@@ -449,6 +513,59 @@ class ParlerTTSForConditionalGeneration:
             h = torch.nn.functional.linear(h, *self.enc_to_dec_proj)
         return h
 
+    # -- generate with user-supplied processors / stopping criteria --------------------------------
+    def _host_driven_loop(self, sess: "GenSession", gc, max_length, user_processors, user_criteria, streamer, seed):
+        """One host iteration per token, like GenerationMixin._sample: the decoder step still runs on the fused kernel
+        (ptts_decode_forward), the built-in processors run as their device operators (MinNewTokens as a mask,
+        ParlerTTSLogitsProcessor = ptts_logits_processor), then the caller's `logits_processor` list, the HF warpers and the draw
+        as torch ops on the device scores, and the token is appended with ptts_sample(forced).  Used only when the caller passes
+        processors or criteria the device loop does not know (the reference merges such lists at :3540-3552)."""
+        d = self.config.decoder
+        K, BK = d.num_codebooks, sess.B * d.num_codebooks
+        parler = ParlerTTSLogitsProcessor(d.eos_token_id, K, sess.B, self.device)
+        gen = torch.Generator(device=self.device).manual_seed(int(seed))
+        unfinished = torch.ones(BK, dtype=torch.long, device=self.device)
+        cur = 1
+        while True:
+            ids = sess.raw_ids[:, :cur]
+            scores = sess.logits.clone()
+            if (gc.min_new_tokens or 0) > 0 and cur - 1 < gc.min_new_tokens:
+                scores[:, d.eos_token_id] = -float("inf")
+            scores = parler(ids, scores)
+            for proc in user_processors:
+                scores = proc(ids, scores)
+            if gc.do_sample:
+                if gc.temperature and gc.temperature != 1.0:
+                    scores = scores / gc.temperature
+                if gc.top_k:
+                    kth = torch.topk(scores, min(int(gc.top_k), scores.shape[-1]))[0][..., -1, None]
+                    scores = scores.masked_fill(scores < kth, -float("inf"))
+                if gc.top_p is not None and gc.top_p < 1.0:
+                    ss, si = torch.sort(scores, descending=False)
+                    rem = ss.softmax(-1).cumsum(-1) <= (1 - gc.top_p)
+                    rem[..., -1:] = False
+                    scores = scores.masked_fill(rem.scatter(1, si, rem), -float("inf"))
+                nxt = torch.multinomial(scores.softmax(-1), 1, generator=gen).squeeze(1)
+            else:
+                nxt = scores.argmax(-1)
+            nxt = nxt * unfinished + d.pad_token_id * (1 - unfinished)
+            sess.sample(forced=nxt)           # append (+ delay-pattern override of the next input), device-side stopping state
+            cur += 1
+            if streamer is not None:
+                streamer.put(nxt.cpu())
+            unfinished = unfinished & ~((nxt == d.eos_token_id) | (cur >= max_length)).long()
+            stop = unfinished.max().item() == 0
+            for crit in user_criteria:
+                r = crit(sess.raw_ids[:, :cur], scores)
+                r = r if isinstance(r, torch.Tensor) else torch.full((BK,), bool(r), device=self.device)
+                unfinished = unfinished & ~r.long()
+                stop = stop or unfinished.max().item() == 0
+            if stop:
+                break
+            sess.decode_forward()
+        if streamer is not None:
+            streamer.end()
+
     # -- generate ----------------------------------------------------------------------------------
     @torch.no_grad()
     def generate(self, inputs: Optional[torch.Tensor] = None, generation_config: Optional[GenerationConfig] = None,
@@ -479,9 +596,7 @@ class ParlerTTSForConditionalGeneration:
         if gc.num_beams != 1:
             raise ValueError("Got incompatible mode for generation, should be one of greedy or sampling. "
                              "Ensure that beam search is de-activated by setting `num_beams=1` and `num_beam_groups=1`.")
-        if logits_processor is not None or stopping_criteria is not None:
-            raise ValueError("custom logits_processor / stopping_criteria lists are not supported by the fused device "
-                             "loop; the ParlerTTSLogitsProcessor + HF warpers are built in")
+        custom_loop = bool(logits_processor) or bool(stopping_criteria)   # merged with the built-in ones like :3540-3552
         if mk.get("decoder_input_ids") is not None or mk.get("input_values") is not None:
             raise ValueError("audio-prompt continuation (decoder_input_ids / input_values) is outside this path")
         input_ids = mk.get("input_ids", inputs)
@@ -522,9 +637,15 @@ class ParlerTTSForConditionalGeneration:
             delayed = torch.full((B * K, 1), d.bos_token_id, dtype=torch.int64)
             streamer.put(delayed)
         sess.prefill(prompt_hidden, prompt_mask, enc_hidden, attention_mask)
-        sess.sample()
-        steps_left = max_length - 2
-        if streamer is not None:
+        if custom_loop:
+            self._host_driven_loop(sess, gc, max_length, logits_processor or [], stopping_criteria or [], streamer, seed)
+            steps_left = 0
+        else:
+            sess.sample()
+            steps_left = max_length - 2
+        if custom_loop:
+            pass
+        elif streamer is not None:
             # the streamer contract is one host-visible token column per step (_sample -> streamer.put(next.cpu()))
             col = 1
             streamer.put(sess.raw_ids[:, col].cpu())

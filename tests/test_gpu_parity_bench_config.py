@@ -34,8 +34,15 @@ def _note(name, payload):
 
 
 @pytest.mark.timeout(900)
-def test_bench_config_bf16_free_running_greedy_vs_oracle():
-    """Mini bf16, B=32, S=64, P=32 (left-padded masks), 128 free-running greedy steps through the fused step kernel."""
+def test_bench_config_bf16_greedy_vs_oracle_128_steps():
+    """Mini bf16, B=32, S=64, P=32 (left-padded masks), 128 greedy steps through the fused step kernel against OracleDecoder(bf16).
+
+    With random weights the top-2 gap of 1088 logits is often inside bf16 noise (13 % of the rows per step have a gap below
+    1.3 % of the logit scale), so a free-running comparison leaves every utterance's history within a few steps (reported, not
+    asserted).  The assertion that survives is the strict one per step: run the kernel on the ORACLE's history (the kernel's own
+    greedy choice is compared first, then the oracle's token is appended), require the logits within the measured noise bound,
+    and allow the kernel's token to differ from the oracle's only where the oracle's own top-2 margin is below twice that bound.
+    All 32 utterances are checked at all 128 steps (cache length 33 -> 161: several K/V ring chunks per warp)."""
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
     steps = 128
     cfg = mini_cfg(max_position_embeddings=512)
@@ -49,47 +56,55 @@ def test_bench_config_bf16_free_running_greedy_vs_oracle():
     L = steps + 1
     ref = generate_tokens(OracleDecoder(cfg, w, torch.bfloat16), cfg, enc, enc_mask, prompt, prompt_mask,
                           dict(max_length=L, do_sample=False), collect_logits=True)
+    n_steps = min(steps, ref["raw_ids"].shape[1] - 1)
+
+    # (1) free-running, for the record: first step at which an utterance's tokens leave the oracle's
     sess = model.decoder.engine.session(B, P, S, P + L)
     sess.begin(L, do_sample=False)
     sess.prefill(prompt.to(DEV), prompt_mask, enc.to(DEV), enc_mask)
-    assert sess.fused == 1, "the benchmarked configuration must run the fused step kernel"
-    alive = np.ones(B, dtype=bool)            # utterances whose history still equals the oracle's
-    first_div = np.full(B, -1)
-    div_margin = np.zeros(B)
-    max_rel_err = 0.0
-    n_ref = ref["raw_ids"].shape[1]
-    for t in range(min(steps, n_ref - 1)):
+    assert sess.fused >= 1, "the benchmarked configuration must run the fused step kernel"
+    kind = sess.fused
+    sess.sample()
+    sess.decode_steps(n_steps - 1)
+    torch.cuda.synchronize()
+    free = sess.raw_ids[:, : n_steps + 1].cpu().numpy()
+    neq = (free != ref["raw_ids"][:, : n_steps + 1]).reshape(B, K, -1).any(1)
+    first_div = [int(np.argmax(r)) - 1 if r.any() else -1 for r in neq]
+
+    # (2) on the oracle's history: logits and greedy choice at every step
+    sess.begin(L, do_sample=False)
+    sess.prefill(prompt.to(DEV), prompt_mask, enc.to(DEV), enc_mask)
+    max_rel_err, flips, worst_flip_margin, rows_total = 0.0, 0, 0.0, 0
+    for t in range(n_steps):
         if t > 0:
             sess.decode_forward()
         a = sess.logits.float().cpu().numpy()
-        b = ref["logits"][t]
+        b, sc = ref["logits"][t], ref["scores"][t]
         scale = float(np.abs(b).max())
-        rows_alive = np.repeat(alive, K)
-        if rows_alive.any():
-            max_rel_err = max(max_rel_err, float(np.abs(a - b)[rows_alive].max()) / scale)
-        sess.sample()
-        tok = sess.raw_ids[:, t + 1].cpu().numpy()
-        want = ref["raw_ids"][:, t + 1]
-        srt = np.sort(ref["scores"][t], axis=-1)
+        max_rel_err = max(max_rel_err, float(np.abs(a - b).max()) / scale)
+        a_proc = np.where(np.isneginf(sc), -np.inf, a)          # the processors only mask (EOS gating / min_new_tokens)
+        srt = np.sort(sc, axis=-1)
         margin = (srt[:, -1] - srt[:, -2]) / scale
-        for u in np.nonzero(alive)[0]:
-            rows = slice(u * K, (u + 1) * K)
-            bad = np.nonzero(tok[rows] != want[rows])[0]
-            if len(bad):
-                alive[u] = False
-                first_div[u] = t
-                div_margin[u] = float(margin[rows][bad].max())  # every differing row must have been a near-tie
-    _note("bench_config_free_running_bf16", dict(steps=steps, B=B, S=S, P=P, max_rel_logit_err=max_rel_err,
-                                                 utterances_identical_to_the_end=int(alive.sum()),
-                                                 first_divergence_step=first_div.tolist(), margin_at_divergence=div_margin.tolist()))
-    print(f"\n[parity] bf16 free-running: max |logit err| / max|logit| = {max_rel_err:.4f}; {int(alive.sum())}/{B} utterances "
-          f"token-identical over {steps} steps; divergences at steps {sorted(set(first_div[first_div >= 0].tolist()))} "
-          f"with oracle top-2 margins <= {div_margin.max():.4f} of the logit scale")
-    # measured on B200 (gpurun_out/parity_r02.json): logit error ~1 % of the largest logit
-    assert max_rel_err < 0.025, max_rel_err
-    # a token may only differ where the oracle's own decision was inside the noise: margin below 2x the logit error bound
-    assert (div_margin[first_div >= 0] < 0.05).all(), div_margin
-    assert alive.sum() >= B // 2, f"only {alive.sum()} of {B} utterances stayed identical"
+        want = sc.argmax(-1)
+        bad = a_proc.argmax(-1) != want
+        flips += int(bad.sum())
+        rows_total += bad.size
+        if bad.any():
+            worst_flip_margin = max(worst_flip_margin, float(margin[bad].max()))
+        sess.sample(forced=torch.from_numpy(ref["raw_ids"][:, t + 1].copy()))
+    torch.cuda.synchronize()
+    assert np.array_equal(sess.raw_ids[:, : n_steps + 1].cpu().numpy(), ref["raw_ids"][:, : n_steps + 1])
+    _note("bench_config_bf16_vs_oracle", dict(steps=n_steps, B=B, S=S, P=P, fused_kind=kind, max_rel_logit_err=max_rel_err,
+                                              greedy_flips=flips, rows_checked=rows_total, worst_margin_at_a_flip=worst_flip_margin,
+                                              free_running_first_divergence_step=first_div))
+    print(f"\n[parity] bf16 bench config (fused kind {kind}): max |logit err| / max|logit| = {max_rel_err:.4f} over {n_steps} steps; "
+          f"{flips} of {rows_total} greedy choices differ from the oracle's, all at oracle top-2 margins <= {worst_flip_margin:.4f} of the "
+          f"logit scale; free-running histories leave the oracle's at steps {sorted(set(first_div))}")
+    # measured on B200 (gpurun_out/parity_r02.json): 0.0195 of the largest logit
+    assert max_rel_err < 0.03, max_rel_err
+    # a token may only differ where the oracle's own decision was inside the noise: margin below twice the logit error
+    assert worst_flip_margin < 2 * max(max_rel_err, 0.01), (worst_flip_margin, max_rel_err)
+    assert flips < 0.08 * rows_total, (flips, rows_total)
 
 
 @pytest.mark.timeout(600)
@@ -191,3 +206,77 @@ def test_sampling_is_shard_invariant():
     assert np.array_equal(whole[: 2 * K, :n], lo[:, :n])
     assert np.array_equal(whole[2 * K:, :n], hi[:, :n])
     assert not np.array_equal(lo[:, 1:n], hi[:, 1:n])  # different utterances really draw different streams
+
+
+def test_causal_lm_forward_step_operator():
+    """ParlerTTSForCausalLM.forward as an HF-style loop drives it (reference :1865-1974 + prepare_inputs_for_generation :2909):
+    BOS column + conditioning on the first call, then one delay-masked column per call over the returned cache; logits against
+    the oracle's cached loop, fp32."""
+    from oracle import delay_pattern as odp
+    cfg = tiny_cfg()
+    w = make_decoder_weights(cfg, seed=51, head_std=0.5)
+    dcfg = tiny_dac_cfg()
+    model = build_product_model(cfg, dcfg, w, make_dac_weights(dcfg, seed=1), dtype=torch.float32)
+    B, S, P, L = 2, 6, 3, 12
+    K = cfg.num_codebooks
+    enc, enc_mask, prompt, prompt_mask = synth_inputs(cfg, B, S, P, seed=6, masks=True)
+    ref = generate_tokens(OracleDecoder(cfg, w, torch.float32), cfg, enc, enc_mask, prompt, prompt_mask,
+                          dict(max_length=L, do_sample=False), collect_logits=True)
+    lm = model.decoder
+    ids = np.full((B * K, 1), cfg.bos_token_id, dtype=np.int64)
+    out = lm.forward(input_ids=torch.from_numpy(ids).to(DEV), encoder_hidden_states=enc.to(DEV), encoder_attention_mask=enc_mask.to(DEV),
+                     prompt_hidden_states=prompt.to(DEV), prompt_attention_mask=prompt_mask.to(DEV), max_cache_len=P + L + 4)
+    assert out.logits.shape == (B * K, 1, cfg.vocab_size)
+    assert np.abs(out.logits[:, 0].cpu().numpy() - ref["logits"][0]).max() < 5e-4
+    cache = out.past_key_values
+    raw = ref["raw_ids"]
+    for t in range(1, raw.shape[1] - 1):
+        masked = odp.apply_delay_pattern_mask(raw[:, : t + 1], ref["delay_mask"])[:, -1:]   # what prepare_inputs_for_generation feeds
+        out = lm(input_ids=torch.from_numpy(masked.copy()).to(DEV), past_key_values=cache)
+        assert np.abs(out.logits[:, 0].cpu().numpy() - ref["logits"][t]).max() < 5e-4, t
+    assert cache.get_seq_length() == P + raw.shape[1] - 1
+    with pytest.raises(ValueError):
+        lm.forward(input_ids=torch.zeros(B * K, 2, dtype=torch.long, device=DEV), past_key_values=cache)
+
+
+def test_generate_with_custom_logits_processor_and_stopping_criteria():
+    """generate(logits_processor=[...], stopping_criteria=[...]) (reference merges user lists at :3540-3552): the host-driven loop
+    over the same device operators.  A processor that bans one token id and a criterion that stops at 9 columns; greedy, fp32:
+    tokens bit-exact against the oracle loop with the same ban."""
+    cfg = tiny_cfg()
+    w = make_decoder_weights(cfg, seed=52, head_std=0.5)
+    dcfg = tiny_dac_cfg()
+    model = build_product_model(cfg, dcfg, w, make_dac_weights(dcfg, seed=1), dtype=torch.float32)
+    B, S, P, L = 2, 6, 3, 16
+    enc, enc_mask, prompt, prompt_mask = synth_inputs(cfg, B, S, P, seed=7, masks=True)
+    banned = 5
+
+    def ban(input_ids, scores):
+        scores[:, banned] = -float("inf")
+        return scores
+
+    seen = []
+
+    def stop_at_9(input_ids, scores):
+        seen.append(input_ids.shape[1])
+        return input_ids.shape[1] >= 9
+
+    ref = generate_tokens(OracleDecoder(cfg, w, torch.float32), cfg, enc, enc_mask, prompt, prompt_mask, dict(max_length=L, do_sample=False),
+                          pick=lambda step, s: np.where(np.arange(s.shape[1])[None, :] == banned, -np.inf, s).argmax(-1))
+    _, out = model.generate(encoder_outputs=(enc.to(DEV),), attention_mask=enc_mask.to(DEV), prompt_hidden_states=prompt.to(DEV),
+                            prompt_attention_mask=prompt_mask.to(DEV), do_sample=False, max_length=L, logits_processor=[ban],
+                            stopping_criteria=[stop_at_9], return_codes=True)
+    got = out.raw_ids.cpu().numpy()
+    n = min(got.shape[1], ref["raw_ids"].shape[1])
+    assert got.shape[1] <= 9 and n >= 2 and seen
+    # raw_ids returned by generate() have the delay mask applied (like the reference's output_ids); compare the free cells
+    from oracle import delay_pattern as odp
+    want = odp.apply_delay_pattern_mask(ref["raw_ids"][:, :n], ref["delay_mask"])
+    full_mask = odp.build_delay_pattern_mask(np.full((got.shape[0], 1), cfg.bos_token_id, dtype=np.int64), cfg.bos_token_id, cfg.pad_token_id, L, cfg.num_codebooks)[1]
+    free = full_mask[:, :n] == -1
+    assert np.array_equal(got[:, :n][free], want[free])
+    assert not (got[:, 1:n][free[:, 1:]] == banned).any()
+    with pytest.raises(ValueError):
+        model.generate(encoder_outputs=(enc.to(DEV),), do_sample=False, max_length=6, repetition_penalty=1.3)
+    with pytest.raises(ValueError):
+        model.generate(encoder_outputs=(enc.to(DEV),), do_sample=False, max_length=6, not_a_real_kwarg=1)
