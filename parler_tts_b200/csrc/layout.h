@@ -35,12 +35,14 @@ struct DecoderLayout {
   int64_t total;
 };
 
-// Shapes the cluster step kernel covers: bf16, MHA for self- and cross-attention, one cluster of 8 CTAs per head (<= 18 heads on
-// 148 SMs), K slices that are whole k32 tiles, and at most 4 fc1 n-tiles per rank (accumulator / exchange-buffer budget).
+// Shapes the cluster step kernel covers: bf16, MHA for self- and cross-attention, two clusters of 4 CTAs per head (<= 18 heads on
+// 148 SMs), K halves that are whole k32 tiles, H / (2 heads) = 32 out-proj features per cluster, at most 4 fc1 n-tiles per rank, and
+// the shared-memory plan of step2.cu (sized for H <= 1024, F <= 4096).
 static inline bool cluster_shape_ok(const ptts_decoder_config& c) {
   const int H = c.hidden_size, nh = c.num_heads, F = c.ffn_dim;
   return c.dtype == PTTS_BF16 && c.num_kv_heads == nh && c.num_cross_kv_heads == nh && nh * 8 <= 144 && H == nh * PTTS_HEAD_DIM &&
-         H % 256 == 0 && F % 256 == 0 && F % (nh * 64) == 0 && F / (nh * 64) <= 4 && H <= 1024 && F <= 4096 && c.num_codebooks <= 16;
+         H % 256 == 0 && F % 256 == 0 && F % (nh * 64) == 0 && F / (nh * 64) <= 4 && H <= 1024 && F <= 4096 && c.num_codebooks <= 16 &&
+         (c.vocab_size * c.num_codebooks) % 32 == 0;
 }
 
 static inline int dtype_size(int dt) { return dt == PTTS_BF16 ? 2 : 4; }
@@ -80,12 +82,14 @@ static inline DecoderLayout make_layout(const ptts_decoder_config& c) {
   l.cl_C = l.cl_NC = 0;
   for (int i = 0; i < 6; i++) l.cp[i] = l.cp_slice[i] = 0;
   if (cluster_shape_ok(c)) {
-    l.cl_C = 8; l.cl_NC = l.nh;
-    const int64_t ks = l.H / 8 / 32, ksf = l.F / 8 / 32;                 // k32 tiles per rank: K = H phases, K = F phase
-    const int64_t nt[6] = {24, 8, 8, 8, l.F / l.nh / 8, 8};               // n-tiles per cluster (head: q|k|v = 192 features; 64; F/nh)
+    l.cl_C = 4; l.cl_NC = 2 * l.nh;
+    const int64_t ks = l.H / 4 / 32, ksf = l.F / 4 / 32;                 // k32 tiles per rank: K = H phases, K = F phase
+    // n-tiles per slice: a head's q|k|v (192 features), a cluster's 32 out-proj features, a head's q_cross, ..., F / 32 fc1 features
+    const int64_t nt[6] = {24, 4, 8, 4, l.F / (2 * l.nh) / 8, 4};
+    const int64_t owners[6] = {l.nh, 2 * l.nh, l.nh, 2 * l.nh, 2 * l.nh, 2 * l.nh};   // head phases: one slice set per head
     for (int i = 0; i < 6; i++) {
       l.cp_slice[i] = nt[i] * (i == 5 ? ksf : ks) * 512;
-      l.cp[i] = take(l.cp_slice[i] * l.cl_NC * l.cl_C) - base;
+      l.cp[i] = take(l.cp_slice[i] * owners[i] * l.cl_C) - base;
     }
   }
   l.layer_stride = o - base;
@@ -140,7 +144,7 @@ struct WorkspaceLayout {
   int64_t ctrl, progress, gen, raw_ids, cur_ids, eos_seen, unfinished, first_unf, prompt_mask, enc_mask;
   int64_t x, qkv, attn, qc, hbuf, hidden, logits, scores, cross_tmp, cross_kv, self_kv;
   int64_t img_x, img_attn, img_h;  // fused step kernel: activations as tile images [chunk][32][H + 8] (step.cu stage_tile)
-  int64_t cl_x, cl_attn, cl_h;     // cluster step kernel: K-sliced images [8][32][K/8 + 8] (step2.cu)
+  int64_t cl_x, cl_attn, cl_h;     // cluster step kernel: K-sliced images [4][32][K/4 + 8] (step2.cu)
   int64_t row_stats;               // [max(B*(P+1), B*S)][2] f32: LayerNorm row statistics of the tcgen05 prefill GEMMs
   int64_t cross_layer_stride, self_layer_stride;  // bytes
   int64_t raw_ld;                                  // raw_ids leading dimension (elements)
@@ -176,9 +180,9 @@ static inline WorkspaceLayout make_workspace(const ptts_decoder_config& c, int B
   w.img_attn = take((int64_t)32 * (l.H + 8) * 2);
   w.img_h = take((int64_t)((l.F + l.H - 1) / l.H) * 32 * (l.H + 8) * 2);
   w.row_stats = take((int64_t)(w.Mmax > rows_enc ? w.Mmax : rows_enc) * 2 * 4);
-  w.cl_x = take((int64_t)8 * 32 * (l.H / 8 + 8) * 2);
-  w.cl_attn = take((int64_t)8 * 32 * (l.H / 8 + 8) * 2);
-  w.cl_h = take((int64_t)8 * 32 * (l.F / 8 + 8) * 2);
+  w.cl_x = take((int64_t)4 * 32 * (l.H / 4 + 8) * 2);
+  w.cl_attn = take((int64_t)4 * 32 * (l.H / 4 + 8) * 2);
+  w.cl_h = take((int64_t)4 * 32 * (l.F / 4 + 8) * 2);
   w.logits = take((int64_t)w.BK * l.V * 4);
   w.scores = take((int64_t)w.BK * l.V * 4);
   w.cross_layer_stride = align_up(rows_enc * l.ckv_rows * l.es, 256);

@@ -37,7 +37,7 @@ struct StepParams {
   long long* prof;         // optional [(8L+3)][8] clock64 timestamps written by CTA 0 (debug / profiles)
   // ---- cluster step kernel (step2.cu) ----
   int64_t cp[6], cp_slice[6];   // per-layer offsets / slice bytes of the (phase, cluster, rank) weight slices (layout.h)
-  bf16 *cl_x, *cl_attn, *cl_h;  // K-sliced activation images [8][32][K/8 + 8]
+  bf16 *cl_x, *cl_attn, *cl_h;  // K-sliced activation images [4][32][K/4 + 8]
 };
 
 int step_smem_bytes(const StepParams& p);

@@ -2,26 +2,28 @@
 //
 // Replaces the same reference code as step.cu (ParlerTTSForCausalLM.forward with q_len == 1, modeling_parler_tts.py:1865-1974 /
 // :983-1074, plus one iteration of GenerationMixin._sample) for the shapes layout.h::cluster_shape_ok() accepts (Parler-TTS-Mini:
-// MHA, one head per cluster).  step.cu's design -- 148 CTAs that each need the WHOLE 32 x H activation tile in every one of the
-// 8 dependent phases of a layer -- measured 6.5 us per phase: ~2 us device-wide barrier, 1.3 us to pull the 66 KB tile, 0.6 us of
-// LayerNorm statistics over it, an 8-warp split-K reduction through shared memory; 4.5 x the HBM time of the bytes it moves
-// (profiles/r01_step_phases.md, r02_step_phases.md).  This kernel cuts the dependent chain and the per-CTA fixed work:
+// MHA, 16 heads).  step.cu's design -- 148 CTAs that each need the WHOLE 32 x H activation tile in every one of the 8 dependent
+// phases of a layer -- measured 6.5 us per phase: ~2 us device-wide barrier, 1.3 us to pull the 66 KB tile, 0.6 us of LayerNorm
+// statistics over it, an 8-warp split-K reduction through shared memory; 4.5 x the HBM time of the bytes it moves
+// (profiles/r01_step_phases.md).  This kernel cuts the dependent chain and the per-CTA fixed work:
 //
-//   * grid = 16 clusters x 8 CTAs (cudaLaunchAttributeClusterDimension).  Cluster c OWNS head c: its q/k/v features, its K/V
-//     cache items, its 64 out-proj / fc2 features and its F/16 fc1 features.  Rank r of a cluster reduces K-slice r (K/8 columns):
-//     a CTA stages 8.7 KB of activations per phase instead of 66 KB, every warp owns whole n-tiles (no split-K through shared
-//     memory), and the eight partial sums are exchanged through DISTRIBUTED SHARED MEMORY with one cp.async.bulk
-//     (shared::cta -> shared::cluster, mbarrier complete_tx) per peer.
-//   * the exchange of a projection that feeds attention is ROW-partitioned (rank r receives rows 4r..4r+3 of q|k|v for head c),
-//     so RoPE, the KV-cache append and the attention of those 4 (row, head) items run inside the same phase:
-//     QKV -> self-attention and q_cross -> cross-attention need no device-wide barrier between them.  6 barriers per layer, not 8.
-//   * the residual stream slice a CTA owns (32 rows x 8 features) never leaves its shared memory.
+//   * grid = 32 clusters x 4 CTAs (cudaLaunchAttributeClusterDimension; this B200 co-schedules only 15 clusters of 8 -- seven
+//     GPCs of 20 SMs and one of 8 -- but 37 clusters of 4).  Every GEMM is split 8 ways along K: rank r of a cluster stages K-slice
+//     r (K/4 columns: 8-17 KB of activations instead of 66 KB) and its two warp groups reduce one half of it each ("virtual
+//     ranks" v = 2 r + half).  Every warp owns whole n-tiles (no split-K through shared memory inside a CTA); the eight partial
+//     sums meet through DISTRIBUTED SHARED MEMORY: one cp.async.bulk (shared::cta -> shared::cluster, mbarrier complete_tx) per peer.
+//   * out-proj / cross out-proj / fc1 / fc2: cluster c owns N/32 output features, rank d finalises a quarter of them
+//     (feature-partitioned exchange).  The residual-stream slice a CTA owns (32 rows x 8 features) never leaves its shared memory.
+//   * QKV and q_cross: clusters 2h and 2h+1 own HEAD h for batch rows 0-15 / 16-31; the exchange is ROW-partitioned (rank d
+//     receives rows 4d..4d+3 of q|k|v), so RoPE, the KV-cache append and the attention of those 4 (row, head) items run inside
+//     the same phase: QKV -> self-attention and q_cross -> cross-attention need no device-wide barrier between them.
+//     6 barriers per layer instead of 8.
 //   * weights: one contiguous slice per (phase, cluster, rank) (layout.h cpack, built once by ptts_decoder_finalize), streamed by
-//     ONE bulk copy into a 2 x 64 KB ring two phases ahead and pulled HBM -> L2 a layer ahead (layer 0 of the NEXT token is
+//     ONE bulk copy per job into a 2 x 64 KB ring two jobs ahead and pulled HBM -> L2 a layer ahead (layer 0 of the NEXT token is
 //     prefetched during the lm-head phase: L2 survives the kernel boundary).
 //   * the activation slice of the next phase is requested by the barrier's polling thread the moment the barrier opens.
-// Reduction orders are fixed (k-tiles ascending inside a CTA, ranks 0..7 across the cluster): bit-reproducible run to run.  They
-// differ from step.cu / gemm.cu, so the two paths agree to bf16 accumulation-order noise, not bitwise (tests/test_gpu_parity.py).
+// Reduction orders are fixed (k-tiles ascending inside a warp, virtual ranks 0..7 across the cluster): bit-reproducible run to
+// run.  They differ from step.cu / gemm.cu, so the two paths agree to bf16 accumulation-order noise, not bitwise.
 #include "attn_core.cuh"
 #include "common.cuh"
 #include "kernels.h"
@@ -32,20 +34,22 @@
 namespace ptts {
 namespace cl {
 
-constexpr int C = 8;            // CTAs per cluster == warps per CTA (warp w produces the block that rank w finalises)
+constexpr int C = 4;            // CTAs per cluster
+constexpr int V = 8;            // virtual ranks = warps per CTA: warp w reduces K-half (w >> 2) for destination rank (w & 3)
 constexpr int THREADS = 256;
-constexpr int ROWS = 32;        // batch rows (two m16 tiles)
+constexpr int ROWS = 32;        // batch rows (two m16 tiles; the head phases work on one half = one m16 tile)
 constexpr int ATT_CH = 16;      // keys per K/V ring stage of an attention warp
-constexpr int HDR = 8192;       // mbarriers | row stats | stat partials | residual slice | folded-LN vectors
+constexpr int QMAX = 6;         // n-tiles per warp (QKV: 24 n-tiles of a head over 4 destination groups)
+constexpr int OFF_STATS = 256, OFF_PART = 512, OFF_RES = 2560, OFF_CVEC = 3584;
+constexpr int HDR = 5632;       // mbarriers | row stats | stat partials | residual slice | folded-LN vectors c1[256] c2[256]
 constexpr int WB_BYTES = 65536; // one weight ring buffer
-constexpr int OFF_STATS = 256, OFF_PART = 512, OFF_RES = 2560, OFF_CVEC = 4096;
 constexpr int R_OFF = HDR + 2 * WB_BYTES;
-// R region: [activation slice | send blocks] (phase dependent split) then the receive slots; attention scratch and the lm-head
-// tile alias all of it.  Sized for Mini (H = 1024, F = 4096): fc1 exchange blocks of 256 B stats + 32 x 36 floats.
-constexpr int U_BYTES = 47616, RECV_BYTES = 38912, R_BYTES = U_BYTES + RECV_BYTES;
+// R region: [activation slice | 8 send blocks | 8 receive slots], split per phase; attention scratch and the lm-head tile alias it.
+// Sized for Mini (H = 1024, F = 4096): fc1 = 16.5 KB slice + 2 x 8 blocks of (256 B stats + 32 x 34 floats).
+constexpr int R_BYTES = 92160;
 constexpr int QKV_OFF = R_BYTES - 2048;   // [4 rows][192] bf16 q|k|v (or [4][64] q_cross) of this rank's attention items
 constexpr int SMEM_BYTES = R_OFF + R_BYTES;
-static_assert(SMEM_BYTES <= 227 * 1024, "cluster step kernel shared memory");
+static_assert(SMEM_BYTES + 1024 <= 227 * 1024, "cluster step kernel shared memory");
 
 // ---- PTX helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,14 +120,19 @@ __device__ __forceinline__ unsigned grid_sync(unsigned* ctr, unsigned target, in
 
 // phase kinds of a layer
 enum { PH_QKV = 0, PH_O = 1, PH_QC = 2, PH_OC = 3, PH_FC1 = 4, PH_FC2 = 5 };
+constexpr int JOBS_PER_LAYER = 7;   // weight jobs: QKV (two halves of 12 n-tiles), O, QC, OC, FC1, FC2
 
-// source of weight job j for this CTA (jobs: 6 per layer in phase order, then this CTA's lm-head tasks)
-__device__ __forceinline__ bool weight_job(const StepParams& p, int j, int cta, const char*& src, uint32_t& bytes) {
-  const int nl = 6 * p.L;
+// source of weight job j for this CTA (7 per layer, then this CTA's lm-head tasks)
+__device__ __forceinline__ bool weight_job(const StepParams& p, int j, int cta, int rank, const char*& src, uint32_t& bytes) {
+  const int nl = JOBS_PER_LAYER * p.L;
   if (j < nl) {
-    const int l = j / 6, ph = j - 6 * l;
-    bytes = (uint32_t)p.cp_slice[ph];
-    src = p.blob + p.layer0 + p.layer_stride * l + p.cp[ph] + (int64_t)cta * p.cp_slice[ph];
+    const int l = j / JOBS_PER_LAYER, jl = j - JOBS_PER_LAYER * l;
+    const int ph = jl < 2 ? 0 : jl - 1;
+    // the head phases' slices are shared by the two row-half clusters of a head: indexed (head, rank)
+    const int64_t idx = (ph == PH_QKV || ph == PH_QC) ? (int64_t)(cta >> 3) * C + rank : (int64_t)cta;
+    const int64_t sz = p.cp_slice[ph];
+    bytes = (uint32_t)(ph == PH_QKV ? sz / 2 : sz);
+    src = p.blob + p.layer0 + p.layer_stride * l + p.cp[ph] + idx * sz + (jl == 1 ? sz / 2 : 0);
     return true;
   }
   const int task = cta + (int)gridDim.x * (j - nl);
@@ -146,11 +155,13 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.H, F = p.F, B = p.B;
   const int rank = (int)cluster_rank();
-  const int cta = (int)blockIdx.x;         // = cluster * 8 + rank
-  const int cluster = cta >> 3;            // == the attention head this cluster owns
-  const int Ks = H / C, KsF = F / C;       // K-slice widths
+  const int cta = (int)blockIdx.x;         // = cluster * 4 + rank
+  const int cluster = cta >> 2;
+  const int head = cluster >> 1, half = cluster & 1;   // head phases: this cluster's head and its batch-row half (rows 16 half ..)
+  const int Ks = H / C, KsF = F / C;       // K-slice widths of a CTA
   const int pitch = Ks + 8, pitchF = KsF + 8;
-  const int qe = F / p.nh / 64;            // fc1 n-tiles per rank (Mini: 4)
+  const int qe = F / p.nh / 64;            // fc1 n-tiles per destination rank (Mini: 4)
+  const int dgrp = warp & 3, kh = warp >> 2;  // this warp: destination group, K half of the CTA's slice
 
   uint64_t* abar = reinterpret_cast<uint64_t*>(smem);        // activation slice
   uint64_t* wbar = abar + 1;                                  // [2] weight ring
@@ -182,45 +193,45 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   // weight ring: job j lives in buffer j & 1; jobs 0 and 1 are requested now, job j + 2 when job j's MMA loop has retired
   auto issue_weight_job = [&](int j) {  // ONE thread
     const char* src; uint32_t bytes;
-    if (!weight_job(p, j, cta, src, bytes)) return;
+    if (!weight_job(p, j, cta, rank, src, bytes)) return;
     fence_proxy_async_smem();
     mbar_expect_tx(&wbar[j & 1], bytes);
     bulk_g2s(smem + HDR + (j & 1) * WB_BYTES, src, bytes, &wbar[j & 1]);
   };
   auto prefetch_weight_job = [&](int j) {  // ONE thread: HBM -> L2, a layer ahead
     const char* src; uint32_t bytes;
-    if (weight_job(p, j, cta, src, bytes)) l2_prefetch(src, bytes);
+    if (weight_job(p, j, cta, rank, src, bytes)) l2_prefetch(src, bytes);
   };
-  // K/V rows of this rank's 4 attention items (rows 4 rank .. 4 rank + 3, head = cluster) -> L2
+  // K/V rows of this rank's 4 attention items (rows 16 half + 4 rank .. + 3, head) -> L2
   auto prefetch_kv = [&](int l, bool cross) {  // ONE thread
     const int T = cross ? p.S : p.Tmax, n = cross ? p.S : pos;
     if (n <= 0) return;
     const char* kc = cross ? p.cross_kv + p.cross_layer_stride * l : p.self_kv + p.self_layer_stride * l;
     const size_t vofs = (size_t)B * p.nh * T * HD * 2;
     for (int i = 0; i < 4; i++) {
-      const int b = 4 * rank + i;
+      const int b = 16 * half + 4 * rank + i;
       if (b >= B) break;
-      const char* k = kc + ((size_t)b * p.nh + cluster) * T * HD * 2;
+      const char* k = kc + ((size_t)b * p.nh + head) * T * HD * 2;
       l2_prefetch(k, (uint32_t)(n * HD * 2));
       l2_prefetch(k + vofs, (uint32_t)(n * HD * 2));
     }
   };
   if (tid == 0) { issue_weight_job(0); issue_weight_job(1); }
-  if (tid == 64) { for (int j = 2; j < 6; j++) prefetch_weight_job(j); prefetch_kv(0, false); prefetch_kv(0, true); }
+  if (tid == 64) { for (int j = 2; j < JOBS_PER_LAYER; j++) prefetch_weight_job(j); prefetch_kv(0, false); prefetch_kv(0, true); }
 
-  // global activation images, K-sliced for their consumer: [8 slices][32 rows][slice width + 8] bf16
-  bf16* const x_img = p.cl_x;       // slices of H/8 columns (consumers: QKV, q_cross, fc1, lm heads)
-  bf16* const a_img = p.cl_attn;    // slices of H/8 columns = 2 heads (consumers: out_proj, cross out_proj)
-  bf16* const h_img = p.cl_h;       // slices of F/8 columns (consumer: fc2)
+  // global activation images, K-sliced for their consumer: [4 slices][32 rows][slice width + 8] bf16
+  bf16* const x_img = p.cl_x;       // slices of H/4 columns (consumers: QKV, q_cross, fc1, lm heads)
+  bf16* const a_img = p.cl_attn;    // slices of H/4 columns = 4 heads (consumers: out_proj, cross out_proj)
+  bf16* const h_img = p.cl_h;       // slices of F/4 columns (consumer: fc2)
   const int x_slice_elems = ROWS * pitch, h_slice_elems = ROWS * pitchF;
-  // where this CTA's 8 residual / out-proj features live in the x image: feature n = cluster * 64 + rank * 8 + f
-  const int xo_slice = (cluster * 64 + rank * 8) / Ks, xo_col = (cluster * 64 + rank * 8) % Ks;
+  // where this CTA's 8 residual / out-proj features live in the x image: feature n = cta * 8 + f
+  const int xo_slice = (cta * 8) / Ks, xo_col = (cta * 8) % Ks;
 
   // ---- embeddings: this CTA's 32 x 8 slice of sum_k embed_k[id] (+ position) -> residual slice + x image -----------------
   {
     const bf16* tables = reinterpret_cast<const bf16*>(blob + p.embed);
     const bf16* postab = p.rope ? nullptr : reinterpret_cast<const bf16*>(blob + p.pos);
-    const int row = tid >> 3, f = tid & 7, n = cluster * 64 + rank * 8 + f;
+    const int row = tid >> 3, f = tid & 7, n = cta * 8 + f;
     float v = 0.f;
     if (row < B) {
       float ev[16];
@@ -236,14 +247,23 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     x_img[(size_t)xo_slice * x_slice_elems + row * pitch + xo_col + f] = __float2bfloat16_rn(v);
   }
   prof_mark(prof, 6);
-  // the first phase's activation slice is requested by the polling thread as soon as the barrier opens
-  auto request_slice = [&](const bf16* img_slice, uint32_t bytes) {  // thread 0
+  auto request_slice = [&](const bf16* img_slice, uint32_t bytes) {  // thread 0, the moment a device-wide barrier opens
     fence_proxy_async_smem();
     mbar_expect_tx(abar, bytes);
     bulk_g2s(Rg, img_slice, bytes, abar);
   };
-  bar_target = grid_sync(bar_ctr, bar_target, -1,
-                         [&]() { request_slice(x_img + (size_t)rank * x_slice_elems, (uint32_t)(x_slice_elems * 2)); }, []() {});
+  // activation slice of phase kind `sub`: rows of this cluster's half for the head phases, all 32 rows otherwise
+  auto slice_of = [&](int sub, const bf16*& img, uint32_t& bytes) {
+    if (sub == PH_QKV || sub == PH_QC) { img = x_img + (size_t)rank * x_slice_elems + (size_t)(16 * half) * pitch; bytes = (uint32_t)(16 * pitch * 2); }
+    else if (sub == PH_O || sub == PH_OC) { img = a_img + (size_t)rank * x_slice_elems; bytes = (uint32_t)(x_slice_elems * 2); }
+    else if (sub == PH_FC1) { img = x_img + (size_t)rank * x_slice_elems; bytes = (uint32_t)(x_slice_elems * 2); }
+    else { img = h_img + (size_t)rank * h_slice_elems; bytes = (uint32_t)(h_slice_elems * 2); }
+  };
+  {
+    const bf16* nimg; uint32_t nbytes;
+    slice_of(PH_QKV, nimg, nbytes);
+    bar_target = grid_sync(bar_ctr, bar_target, -1, [&]() { request_slice(nimg, nbytes); }, []() {});
+  }
   prof_mark(prof, 7);
 
   const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol = (lane >> 4) * 8;
@@ -258,16 +278,19 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     const char* lb = blob + p.layer0 + p.layer_stride * l;
     const bool rowpart = (sub == PH_QKV || sub == PH_QC);
     const bool has_ln = (sub == PH_QKV || sub == PH_QC || sub == PH_FC1);
-    const int q = (sub == PH_QKV) ? 3 : (sub == PH_FC1 ? qe : 1);   // n-tiles per warp
-    const int Nc = C * q * 8;                                        // features of this cluster in this phase
-    const int KT = (sub == PH_FC2 ? KsF : Ks) >> 5;                  // k32 tiles of this rank's slice
+    const int MT = rowpart ? 1 : 2;                                  // m16 tiles (the head phases see one row half)
+    const int q = (sub == PH_QKV) ? 6 : (sub == PH_QC ? 2 : (sub == PH_FC1 ? qe : 1));   // n-tiles per warp
+    const int Nc = 4 * q * 8;                                        // features of this cluster in this phase
+    const int KT = (sub == PH_FC2 ? KsF : Ks) >> 5;                  // k32 tiles of this CTA's slice; a warp reduces half of them
     const int apitch = (sub == PH_FC2) ? pitchF : pitch;
-    const int act_bytes = ROWS * apitch * 2;
-    // exchange geometry
-    const int RS = (q == 1) ? 8 : 8 * q + 4;                         // floats per row of a feature-partitioned block
+    const int act_bytes = (rowpart ? 16 : ROWS) * apitch * 2;
+    // exchange geometry: block (destination rank d, K half) at index 2 d + kh
+    const int RS = (q == 1) ? 8 : 8 * q + 2;                         // floats per row of a feature-partitioned block
     const int blk = rowpart ? (32 + 4 * Nc * 4) : (256 + ROWS * RS * 4);
     unsigned char* send = Rg + ((act_bytes + 127) & ~127);
-    unsigned char* recv = Rg + U_BYTES;
+    unsigned char* recv = send + ((V * blk + 127) & ~127);
+    const int j0 = JOBS_PER_LAYER * l + (sub == 0 ? 0 : sub + 1);    // first weight job of this phase
+    const int njobs = sub == 0 ? 2 : 1;
 
     // folded-LayerNorm vectors of this phase's features (read after two CTA barriers)
     if (has_ln) {
@@ -278,122 +301,133 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       const int nown = rowpart ? Nc : 8 * q;
       if (tid < nown) {
         int n;
-        if (sub == PH_QKV) n = (tid >> 6) * (p.nh * HD) + cluster * HD + (tid & 63);
-        else if (sub == PH_QC) n = cluster * HD + tid;
-        else n = cluster * (F / p.nh) + rank * 8 * q + tid;
+        if (sub == PH_QKV) n = (tid >> 6) * (p.nh * HD) + head * HD + (tid & 63);
+        else if (sub == PH_QC) n = head * HD + tid;
+        else n = cta * 8 * q + tid;
         cvec[tid] = c1[n];
         cvec[256 + tid] = c1[ntot + n];
       }
     }
 
-    // ---- MMA: this warp's q n-tiles over the rank's K slice ----
-    mbar_wait(&wbar[ph & 1], (par_w >> (ph & 1)) & 1u, 1);
-    par_w ^= 1u << (ph & 1);
+    // ---- MMA: this warp's q n-tiles (destination group dgrp) over its half of the CTA's K slice ----
+    for (int i = 0; i < njobs; i++) {
+      mbar_wait(&wbar[(j0 + i) & 1], (par_w >> ((j0 + i) & 1)) & 1u, 1);
+      par_w ^= 1u << ((j0 + i) & 1);
+    }
     mbar_wait(abar, par_a, 0);
     par_a ^= 1u;
     prof_mark(prof, 1);
-    float acc[2][4][4];
+    float acc[2][QMAX][4];
 #pragma unroll
     for (int a = 0; a < 2; a++)
 #pragma unroll
-      for (int j = 0; j < 4; j++)
+      for (int j = 0; j < QMAX; j++)
 #pragma unroll
         for (int e = 0; e < 4; e++) acc[a][j][e] = 0.f;
     RowStatFrag rst;
     row_stat_zero(rst);
     {
       const bf16* xs = reinterpret_cast<const bf16*>(Rg);
-      const uint4* wb = reinterpret_cast<const uint4*>(smem + HDR + (ph & 1) * WB_BYTES) + (size_t)(warp * q) * KT * 32 + lane;
-      for (int kt = 0; kt < KT; kt++) {
+      // QKV: destination groups 0,1 read the first weight job (n-tiles 0..11), groups 2,3 the second (12..23)
+      const int wjob = (sub == PH_QKV) ? j0 + (dgrp >> 1) : j0;
+      const int nt0 = (sub == PH_QKV) ? (dgrp & 1) * q : dgrp * q;   // first n-tile of this warp inside that job's slice
+      const uint4* wb = reinterpret_cast<const uint4*>(smem + HDR + (wjob & 1) * WB_BYTES) + (size_t)nt0 * KT * 32 + lane;
+      const int kt_lo = kh * (KT >> 1), kt_hi = kt_lo + (KT >> 1);
+      for (int kt = kt_lo; kt < kt_hi; kt++) {
         uint32_t a[2][2][4];
 #pragma unroll
         for (int mt = 0; mt < 2; mt++)
+          if (mt < MT) {
 #pragma unroll
-          for (int j = 0; j < 2; j++) ldsm4(a[mt][j], xs + (size_t)(mt * 16 + lrow) * apitch + kt * 32 + j * 16 + lcol);
-        if (has_ln && (kt & 7) == warp) {  // row statistics of k-tile kt ride on the fragments already loaded
+            for (int j = 0; j < 2; j++) ldsm4(a[mt][j], xs + (size_t)(mt * 16 + lrow) * apitch + kt * 32 + j * 16 + lcol);
+          }
+        if (has_ln && (kt & 3) == dgrp) {  // row statistics of k-tile kt ride on the fragments already loaded (one warp per k-tile)
 #pragma unroll
-          for (int mt = 0; mt < 2; mt++) { row_stat_mma(rst, mt, a[mt][0]); row_stat_mma(rst, mt, a[mt][1]); }
+          for (int mt = 0; mt < 2; mt++)
+            if (mt < MT) { row_stat_mma(rst, mt, a[mt][0]); row_stat_mma(rst, mt, a[mt][1]); }
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < QMAX; j++) {
           if (j < q) {
             const uint4 w = wb[((size_t)j * KT + kt) * 32];
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++) {
-              mma_bf16_16816(acc[mt][j], a[mt][0], w.x, w.y);
-              mma_bf16_16816(acc[mt][j], a[mt][1], w.z, w.w);
-            }
+            for (int mt = 0; mt < 2; mt++)
+              if (mt < MT) {
+                mma_bf16_16816(acc[mt][j], a[mt][0], w.x, w.y);
+                mma_bf16_16816(acc[mt][j], a[mt][1], w.z, w.w);
+              }
           }
         }
       }
     }
     prof_mark(prof, 2);
-    __syncthreads();  // activation slice and weight buffer are dead
-    if (tid == 32) {  // refill the ring two jobs ahead; pull the same phase of the next layer (or the lm heads) into L2
-      issue_weight_job(ph + 2);
-      prefetch_weight_job(ph + 6);
+    __syncthreads();  // activation slice and weight buffer(s) are dead
+    if (tid == 32) {  // refill the ring two jobs ahead; pull the same jobs of the next layer (or the lm heads) into L2
+      for (int i = 0; i < njobs; i++) { issue_weight_job(j0 + i + 2); prefetch_weight_job(j0 + i + JOBS_PER_LAYER); }
       if (sub == PH_O && l + 1 < p.L) prefetch_kv(l + 1, false);
       if (sub == PH_OC && l + 1 < p.L) prefetch_kv(l + 1, true);
     }
     cluster_wait();  // every peer is past its previous exchange: my send blocks have been read, its receive slots are free
 
     // ---- partial sums -> send blocks ----
-    if (has_ln) row_stat_store(rst, part, warp, lane);
-    if (!rowpart) {   // block w = [stats 32x2][32 rows][RS]: everything rank w finalises
-      float* blkp = reinterpret_cast<float*>(send + (size_t)warp * blk + 256);
+    if (has_ln) row_stat_store(rst, part, warp, lane);   // (for MT == 1 the second m-tile's entries are zero and never read)
+    if (!rowpart) {   // block (dgrp, kh) = [stats 32x2][32 rows][RS]: what rank dgrp finalises, this K half's share
+      float* blkp = reinterpret_cast<float*>(send + (size_t)(2 * dgrp + kh) * blk + 256);
 #pragma unroll
       for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < QMAX; j++) {
           if (j < q) {
             float* base = blkp + (size_t)(mt * 16 + g) * RS + j * 8 + 2 * t4;
             *reinterpret_cast<float2*>(base) = make_float2(acc[mt][j][0], acc[mt][j][1]);
             *reinterpret_cast<float2*>(base + 8 * RS) = make_float2(acc[mt][j][2], acc[mt][j][3]);
           }
         }
-    } else {          // block d = [stats 4x2][4 rows][Nc]: rows 4d..4d+3, all of the head's features
+    } else {          // block (d, kh) = [stats 4x2][4 rows][Nc]: rows 4d..4d+3 of this cluster's half, all of the head's features
 #pragma unroll
-      for (int mt = 0; mt < 2; mt++)
+      for (int j = 0; j < QMAX; j++) {
+        if (j < q) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          if (j < q) {
-#pragma unroll
-            for (int hh = 0; hh < 2; hh++) {
-              const int row = mt * 16 + g + 8 * hh, col = (warp * q + j) * 8 + 2 * t4;
-              float* dst = reinterpret_cast<float*>(send + (size_t)(row >> 2) * blk + 32) + (row & 3) * Nc + col;
-              *reinterpret_cast<float2*>(dst) = make_float2(acc[mt][j][2 * hh], acc[mt][j][2 * hh + 1]);
-            }
+          for (int hh = 0; hh < 2; hh++) {
+            const int row = g + 8 * hh, col = (dgrp * q + j) * 8 + 2 * t4;
+            float* dst = reinterpret_cast<float*>(send + (size_t)(2 * (row >> 2) + kh) * blk + 32) + (row & 3) * Nc + col;
+            *reinterpret_cast<float2*>(dst) = make_float2(acc[0][j][2 * hh], acc[0][j][2 * hh + 1]);
           }
         }
-    }
-    __syncthreads();
-    if (has_ln && tid < ROWS) {  // this CTA's partial (S1, S2) of row tid over its K slice -> into every block that needs it
-      float S1 = 0.f, S2 = 0.f;
-      const int nw = KT < 8 ? KT : 8;
-      for (int w = 0; w < nw; w++) { S1 += part[((size_t)w * 32 + tid) * 2]; S2 += part[((size_t)w * 32 + tid) * 2 + 1]; }
-      if (!rowpart) {
-#pragma unroll
-        for (int d = 0; d < C; d++) *reinterpret_cast<float2*>(send + (size_t)d * blk + tid * 8) = make_float2(S1, S2);
-      } else {
-        *reinterpret_cast<float2*>(send + (size_t)(tid >> 2) * blk + (tid & 3) * 8) = make_float2(S1, S2);
       }
     }
     __syncthreads();
-    if (tid < C && tid != rank) {  // one DSMEM bulk copy per peer: my block for rank `tid` -> its receive slot [my rank]
-      fence_proxy_async_smem();
-      bulk_s2peer(mapa(s32(recv + (size_t)rank * blk), (uint32_t)tid), send + (size_t)tid * blk, (uint32_t)blk, mapa(s32(xbar), (uint32_t)tid));
+    if (has_ln && tid < ROWS) {  // this CTA's partial (S1, S2) of row tid over its K slice: into the kh = 0 block headers (0 in kh = 1)
+      float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < V; w++) { S1 += part[((size_t)w * 32 + tid) * 2]; S2 += part[((size_t)w * 32 + tid) * 2 + 1]; }
+      if (!rowpart) {
+#pragma unroll
+        for (int d = 0; d < C; d++) {
+          *reinterpret_cast<float2*>(send + (size_t)(2 * d) * blk + tid * 8) = make_float2(S1, S2);
+          *reinterpret_cast<float2*>(send + (size_t)(2 * d + 1) * blk + tid * 8) = make_float2(0.f, 0.f);
+        }
+      } else if (tid < 16) {
+        *reinterpret_cast<float2*>(send + (size_t)(2 * (tid >> 2)) * blk + (tid & 3) * 8) = make_float2(S1, S2);
+        *reinterpret_cast<float2*>(send + (size_t)(2 * (tid >> 2) + 1) * blk + (tid & 3) * 8) = make_float2(0.f, 0.f);
+      }
     }
-    if (tid == C) mbar_expect_tx(xbar, (uint32_t)((C - 1) * blk));
+    __syncthreads();
+    if (tid < C && tid != rank) {  // one DSMEM bulk copy per peer: both K-half blocks for rank `tid` -> its receive slots [2 rank, 2 rank + 1]
+      fence_proxy_async_smem();
+      bulk_s2peer(mapa(s32(recv + (size_t)(2 * rank) * blk), (uint32_t)tid), send + (size_t)(2 * tid) * blk, (uint32_t)(2 * blk), mapa(s32(xbar), (uint32_t)tid));
+    }
+    if (tid == C) mbar_expect_tx(xbar, (uint32_t)((C - 1) * 2 * blk));
     mbar_wait(xbar, par_x, 2);
     par_x ^= 1u;
     prof_mark(prof, 3);
 
-    // ---- epilogue: sum the 8 partial blocks in rank order, LayerNorm fix-up, activation / residual ----
-    auto block_of = [&](int src) -> const unsigned char* { return (src == rank) ? send + (size_t)rank * blk : recv + (size_t)src * blk; };
+    // ---- epilogue: sum the 8 partial blocks in virtual-rank order, LayerNorm fix-up, activation / residual ----
+    auto block_of = [&](int v) -> const unsigned char* { return ((v >> 1) == rank) ? send + (size_t)v * blk : recv + (size_t)v * blk; };
     if (!rowpart) {
       if (has_ln && tid < ROWS) {
         float S1 = 0.f, S2 = 0.f;
-        for (int s = 0; s < C; s++) { const float2 v = *reinterpret_cast<const float2*>(block_of(s) + tid * 8); S1 += v.x; S2 += v.y; }
+        for (int v = 0; v < V; v++) { const float2 x = *reinterpret_cast<const float2*>(block_of(v) + tid * 8); S1 += x.x; S2 += x.y; }
         const float mean = S1 / (float)H;
         stats[2 * tid] = mean;
         stats[2 * tid + 1] = rsqrtf(fmaxf(S2 / (float)H - mean * mean, 0.f) + p.eps);
@@ -405,11 +439,11 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
           const int f = f0 + 8 * i;
           float v = 0.f;
 #pragma unroll
-          for (int s = 0; s < C; s++) v += reinterpret_cast<const float*>(block_of(s) + 256)[row * RS + f];
+          for (int s = 0; s < V; s++) v += reinterpret_cast<const float*>(block_of(s) + 256)[row * RS + f];
           if (sub == PH_FC1) {
             v = stats[2 * row + 1] * (v - stats[2 * row] * cvec[f]) + cvec[256 + f];
             v = apply_act(DT<bf16>::rnd(v), p.act);
-            const int n = cluster * (F / p.nh) + rank * 8 * q + f;   // h feature -> slice n / KsF of the fc2 image
+            const int n = cta * 8 * q + f;   // h feature -> slice n / KsF of the fc2 image
             h_img[(size_t)(n / KsF) * h_slice_elems + row * pitchF + (n % KsF)] = __float2bfloat16_rn(v);
           } else {  // out-proj / cross out-proj / fc2: residual add on the slice this CTA owns
             v = DT<bf16>::rnd(res_s[row * 8 + f] + DT<bf16>::rnd(v));
@@ -419,9 +453,9 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         }
       }
     } else {
-      if (tid < 4) {  // rows 4 rank + tid
+      if (tid < 4) {  // rows 16 half + 4 rank + tid
         float S1 = 0.f, S2 = 0.f;
-        for (int s = 0; s < C; s++) { const float2 v = *reinterpret_cast<const float2*>(block_of(s) + tid * 8); S1 += v.x; S2 += v.y; }
+        for (int v = 0; v < V; v++) { const float2 x = *reinterpret_cast<const float2*>(block_of(v) + tid * 8); S1 += x.x; S2 += x.y; }
         const float mean = S1 / (float)H;
         stats[2 * tid] = mean;
         stats[2 * tid + 1] = rsqrtf(fmaxf(S2 / (float)H - mean * mean, 0.f) + p.eps);
@@ -432,13 +466,13 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         const int r4 = idx / Nc, col = idx - r4 * Nc;
         float v = 0.f;
 #pragma unroll
-        for (int s = 0; s < C; s++) v += reinterpret_cast<const float*>(block_of(s) + 32)[r4 * Nc + col];
+        for (int s = 0; s < V; s++) v += reinterpret_cast<const float*>(block_of(s) + 32)[r4 * Nc + col];
         v = stats[2 * r4 + 1] * (v - stats[2 * r4] * cvec[col]) + cvec[256 + col];
         qkv_s[idx] = __float2bfloat16_rn(v);
       }
     }
     prof_mark(prof, 4);
-    __syncthreads();   // receive slots and this CTA's reads of its own send block are done (and q|k|v complete)
+    __syncthreads();   // receive slots and this CTA's reads of its own send blocks are done (and q|k|v complete)
     cluster_arrive();
     if (rowpart) {
       // attention scratch aliases the send blocks: the peers must have RECEIVED them (each is past its exchange wait) first
@@ -453,12 +487,13 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       a.past_from_ctrl = 0; a.past_len = pos; a.prefix = p.P;
       a.rope = p.rope; a.rope_cos = blob + p.rope_cos; a.rope_sin = blob + p.rope_sin; a.scale = p.scale;
       const bf16* qkv_s = reinterpret_cast<const bf16*>(Rg + QKV_OFF);
-      // row b = 4 rank + i, head = cluster: q at qkv_s[i][0..63] (k at +64, v at +128 for the self phase)
-      const bf16* qbase = qkv_s - (size_t)(4 * rank) * Nc - (size_t)cluster * HD;
+      const int row_base = 16 * half + 4 * rank;
+      // row b = row_base + i, head: q at qkv_s[i][0..63] (k at +64, v at +128 for the self phase)
+      const bf16* qbase = qkv_s - (size_t)row_base * Nc - (size_t)head * HD;
       a.q = qbase; a.ldq = Nc; a.q_col0 = 0;
-      // attn image: row b, head h -> slice h / 2, column (h % 2) * 64
+      // attn image: row b, head h -> slice h / 4, column (h % 4) * 64
       a.ldo = pitch;
-      a.out = a_img + (size_t)(cluster >> 1) * x_slice_elems + (cluster & 1) * HD - (size_t)cluster * HD;
+      a.out = a_img + (size_t)(head >> 2) * x_slice_elems + (head & 3) * HD - (size_t)head * HD;
       if (sub == PH_QKV) {
         a.knew = qbase; a.vnew = qbase; a.ldkv = Nc; a.k_col0 = HD; a.v_col0 = 2 * HD;
         char* kc = p.self_kv + p.self_layer_stride * l;
@@ -475,22 +510,19 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         a.cross = 1; a.kv_len = p.S; a.kv_capacity = p.S;
       }
       const int pair = warp >> 1, part_i = warp & 1;
-      const int b = 4 * rank + pair;
+      const int b = row_base + pair;
       unsigned char* region = Rg + (size_t)warp * attn_decode_smem_per_warp<bf16, ATT_CH>();
-      float* xch = reinterpret_cast<float*>(Rg + (size_t)C * attn_decode_smem_per_warp<bf16, ATT_CH>()) + pair * 128;
-      if (b < B) attention_decode_item_warp<bf16, ATT_CH>(a, b, cluster, pos, region, attbars + 2 * warp, lane, att_parity, part_i, 2, xch, pair + 1);
+      float* xch = reinterpret_cast<float*>(Rg + (size_t)V * attn_decode_smem_per_warp<bf16, ATT_CH>()) + pair * 128;
+      if (b < B) attention_decode_item_warp<bf16, ATT_CH>(a, b, head, pos, region, attbars + 2 * warp, lane, att_parity, part_i, 2, xch, pair + 1);
       prof_mark(prof, 5);
     }
     prof_mark(prof, 6);
 
     // ---- device-wide barrier; the next phase's activation slice is requested the moment it opens ----
-    const int nsub = (sub + 1) % 6;
     const bool last = (ph + 1 == n_phases);
     const bf16* nimg; uint32_t nbytes;
-    if (last) { nimg = x_img; nbytes = (uint32_t)(C * x_slice_elems * 2); }                       // lm heads: the whole x image
-    else if (nsub == PH_O || nsub == PH_OC) { nimg = a_img + (size_t)rank * x_slice_elems; nbytes = (uint32_t)(x_slice_elems * 2); }
-    else if (nsub == PH_FC2) { nimg = h_img + (size_t)rank * h_slice_elems; nbytes = (uint32_t)(h_slice_elems * 2); }
-    else { nimg = x_img + (size_t)rank * x_slice_elems; nbytes = (uint32_t)(x_slice_elems * 2); }
+    if (last) { nimg = x_img; nbytes = (uint32_t)(C * x_slice_elems * 2); }   // lm heads: the whole x image
+    else slice_of((sub + 1) % 6, nimg, nbytes);
     bar_target = grid_sync(bar_ctr, bar_target, ph, [&]() { request_slice(nimg, nbytes); }, []() {});
     prof_mark(prof, 7);
   }
@@ -504,17 +536,17 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     const float* c1 = reinterpret_cast<const float*>(blob + p.c_heads);
     const float* c2 = c1 + p.K * p.V;
     if (tid == 64) {  // layer 0 of the NEXT token -> L2 (the cache outlives the kernel): its first phases start warm
-      for (int j = 0; j < 6; j++) prefetch_weight_job(j);
+      for (int j = 0; j < JOBS_PER_LAYER; j++) prefetch_weight_job(j);
     }
     mbar_wait(abar, par_a, 3);
     par_a ^= 1u;
-    const bf16* xs = reinterpret_cast<const bf16*>(Rg);   // [8 slices][32][pitch]
-    const int KTH = H >> 5;                                // k32 tiles of the full row
+    const bf16* xs = reinterpret_cast<const bf16*>(Rg);   // [4 slices][32][pitch]
+    const int KTH = H >> 5, KTS = Ks >> 5;                 // k32 tiles of the full row / of one slice
     {  // row statistics over the full rows: k-tile kt by warp kt % 8
       RowStatFrag rst;
       row_stat_zero(rst);
       for (int kt = warp; kt < KTH; kt += 8) {
-        const bf16* sl = xs + (size_t)(kt / (Ks >> 5)) * x_slice_elems + (kt % (Ks >> 5)) * 32;
+        const bf16* sl = xs + (size_t)(kt / KTS) * x_slice_elems + (kt % KTS) * 32;
 #pragma unroll
         for (int mt = 0; mt < 2; mt++)
 #pragma unroll
@@ -531,8 +563,8 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     }
     prof_mark(prof, 1);
     float* red = reinterpret_cast<float*>(Rg + (size_t)C * x_slice_elems * 2);  // [4 n-tiles][32][8] partials of the upper K half
-    const int jn = warp >> 1, kh = warp & 1;   // this warp: n-tile jn of the task, K half kh
-    int job = n_phases;
+    const int jn = warp >> 1, khh = warp & 1;   // this warp: n-tile jn of the task, K half khh
+    int job = JOBS_PER_LAYER * p.L;
     for (int task = cta; task < ntasks; task += (int)gridDim.x, job++) {
       mbar_wait(&wbar[job & 1], (par_w >> (job & 1)) & 1u, 4);
       par_w ^= 1u << (job & 1);
@@ -542,8 +574,8 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
 #pragma unroll
         for (int e = 0; e < 4; e++) acc[a][e] = 0.f;
       const uint4* wb = reinterpret_cast<const uint4*>(smem + HDR + (job & 1) * WB_BYTES) + (size_t)jn * KTH * 32 + lane;
-      for (int kt = kh * (KTH / 2); kt < (kh + 1) * (KTH / 2); kt++) {
-        const bf16* sl = xs + (size_t)(kt / (Ks >> 5)) * x_slice_elems + (kt % (Ks >> 5)) * 32;
+      for (int kt = khh * (KTH / 2); kt < (khh + 1) * (KTH / 2); kt++) {
+        const bf16* sl = xs + (size_t)(kt / KTS) * x_slice_elems + (kt % KTS) * 32;
         const uint4 w = wb[(size_t)kt * 32];
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
@@ -554,7 +586,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
           mma_bf16_16816(acc[mt], a1, w.z, w.w);
         }
       }
-      if (kh == 1) {
+      if (khh == 1) {
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
           float* base = red + ((size_t)jn * 32 + mt * 16 + g) * 8 + 2 * t4;
@@ -564,7 +596,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       }
       __syncthreads();  // weight buffer dead, upper-half partials visible
       if (tid == 32) issue_weight_job(job + 2);
-      if (kh == 0) {
+      if (khh == 0) {
         const int n0 = task * 32 + jn * 8 + 2 * t4;
         const float2 c1v = *reinterpret_cast<const float2*>(c1 + n0), c2v = *reinterpret_cast<const float2*>(c2 + n0);
 #pragma unroll
@@ -608,18 +640,19 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   }
 }
 
-// ---- weight repack: fragment-order matrices -> one contiguous slice per (phase, cluster, rank) --------------------------
+// ---- weight repack: fragment-order matrices -> one contiguous slice per (phase, cluster or head, rank) -------------------
 // Both layouts are made of the same 512-byte (n8 x k32) tiles, so the repack is a tile gather.
+//   head phases (QKV, q_cross): slice (head, rank) = the head's n-tiles x k-tiles [rank kts, (rank + 1) kts)
+//   the others: slice cta = cluster * 4 + rank = the cluster's ntc n-tiles x the rank's k-tiles
 __global__ void cluster_pack_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int ph, int nh, int ntc, int kts, int KT_src) {
-  // dst tile index = ((cta * ntc + j) * kts + ktl);  cta = cluster * 8 + rank
-  const int64_t tile = blockIdx.x;
+  const int64_t tile = blockIdx.x;   // dst tile index = (slice * ntc + j) * kts + ktl
   const int ktl = (int)(tile % kts);
   const int j = (int)((tile / kts) % ntc);
-  const int cta = (int)(tile / ((int64_t)kts * ntc));
-  const int cluster = cta >> 3, rank = cta & 7;
+  const int slice = (int)(tile / ((int64_t)kts * ntc));
+  const int rank = slice & 3, owner = slice >> 2;   // owner = head (head phases) or cluster
   int n_tile;
-  if (ph == PH_QKV) n_tile = (j >> 3) * (nh * 8) + cluster * 8 + (j & 7);   // q | k | v rows of head `cluster` in the fused matrix
-  else n_tile = cluster * ntc + j;
+  if (ph == PH_QKV) n_tile = (j >> 3) * (nh * 8) + owner * 8 + (j & 7);   // q | k | v rows of head `owner` in the fused matrix
+  else n_tile = owner * ntc + j;
   const int kt = rank * kts + ktl;
   dst[tile * 32 + threadIdx.x] = src[((int64_t)n_tile * KT_src + kt) * 32 + threadIdx.x];
 }
@@ -629,12 +662,13 @@ __global__ void cluster_pack_kernel(const uint4* __restrict__ src, uint4* __rest
 // ---- host side ----------------------------------------------------------------------------------
 int cluster_pack_layer(const char* layer_src, char* layer_dst, const int64_t* mat_off, const int64_t* cp_off, int nh, int H, int F, cudaStream_t st) {
   // mat_off: byte offsets (inside the layer) of wqkv, wo, wqc, woc, fc1, fc2; cp_off: of the six packed regions
-  const int ks = H / 8 / 32, ksf = F / 8 / 32;
-  const int ntc[6] = {24, 8, 8, 8, F / nh / 8, 8};
+  const int ks = H / 4 / 32, ksf = F / 4 / 32;
+  const int ntc[6] = {24, 4, 8, 4, F / (2 * nh) / 8, 4};
+  const int owners[6] = {nh, 2 * nh, nh, 2 * nh, 2 * nh, 2 * nh};
   for (int ph = 0; ph < 6; ph++) {
     const int kts = (ph == 5) ? ksf : ks;
     const int KT_src = (ph == 5) ? F / 32 : H / 32;
-    const int64_t tiles = (int64_t)nh * 8 * ntc[ph] * kts;
+    const int64_t tiles = (int64_t)owners[ph] * 4 * ntc[ph] * kts;
     cl::cluster_pack_kernel<<<(unsigned)tiles, 32, 0, st>>>(reinterpret_cast<const uint4*>(layer_src + mat_off[ph]),
                                                             reinterpret_cast<uint4*>(layer_dst + cp_off[ph]), ph, nh, ntc[ph], kts, KT_src);
   }
@@ -650,7 +684,7 @@ static const void* cluster_kernel_fn(const StepParams& p) {
 
 static void cluster_launch_config(const StepParams& p, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, cudaStream_t st) {
   cfg = cudaLaunchConfig_t{};
-  cfg.gridDim = dim3((unsigned)(p.nh * cl::C));
+  cfg.gridDim = dim3((unsigned)(2 * p.nh * cl::C));   // 2 clusters per head
   cfg.blockDim = dim3(cl::THREADS);
   cfg.dynamicSmemBytes = cl::SMEM_BYTES;
   cfg.stream = st;
@@ -662,13 +696,13 @@ static void cluster_launch_config(const StepParams& p, cudaLaunchConfig_t& cfg, 
   cfg.numAttrs = 2;
 }
 
-// true when the 16 x 8 cluster grid can be co-resident on this device
+// true when the 32 x 4 cluster grid can be co-resident on this device
 bool cluster_step_available(const StepParams& p) {
   const void* fn = cluster_kernel_fn(p);
   static bool told = false;
   auto why = [&](const char* what, cudaError_t e, int n) {
     if (!told) fprintf(stderr, "ptts_b200: cluster step kernel not used (%s: %s, %d co-resident clusters of %d, need %d); the 148-CTA step kernel runs instead\n",
-                       what, cudaGetErrorString(e), n, cl::C, p.nh);
+                       what, cudaGetErrorString(e), n, cl::C, 2 * p.nh);
     told = true;
     cudaGetLastError();
     return false;
@@ -681,7 +715,7 @@ bool cluster_step_available(const StepParams& p) {
   int n = 0;
   e = cudaOccupancyMaxActiveClusters(&n, fn, &cfg);
   if (e != cudaSuccess) return why("cluster occupancy query", e, n);
-  if (n < p.nh) return why("too few co-resident clusters", cudaSuccess, n);
+  if (n < 2 * p.nh) return why("too few co-resident clusters", cudaSuccess, n);
   return true;
 }
 

@@ -445,6 +445,7 @@ def test_mini_shape_bf16_batch32_teacher_forced():
 # ---- fused persistent step kernel (step.cu) vs the multi-kernel path -------------------------------
 def _free_run_bf16(cfg, w, B, S, P, L, fused, monkeypatch, gen=None, seed=3):
     monkeypatch.setenv("PTTS_FUSED", "1" if fused else "0")
+    monkeypatch.setenv("PTTS_STEP", "legacy")   # step.cu: the kernel that shares its reduction order with the multi-kernel path
     dcfg = tiny_dac_cfg(n_codebooks=cfg.num_codebooks, codebook_size=cfg.codebook_size)
     model = build_product_model(cfg, dcfg, w, make_dac_weights(dcfg, seed=1), dtype=torch.bfloat16)
     enc, enc_mask, prompt, prompt_mask = synth_inputs(cfg, B, S, P, seed=seed)
@@ -490,6 +491,65 @@ def test_fused_step_mini_shape_batch32(monkeypatch):
     b_ids, b_log, _ = _free_run_bf16(cfg, w, 32, 16, 8, 22, False, monkeypatch)
     assert np.array_equal(a_ids, b_ids)
     assert np.array_equal(a_log, b_log)
+
+
+def test_cluster_step_kernel_matches_legacy_step_kernel(monkeypatch):
+    """step2.cu (32 clusters x 4 CTAs, K split 8 ways, DSMEM exchange, attention fused into the projection phases) against step.cu
+    on the Mini layer shape, B=32: same inputs, teacher-forced on the legacy kernel's greedy tokens.  The two kernels add the same
+    products in a different order, so the logits agree to bf16 accumulation noise and the greedy choice wherever it is clear."""
+    cfg = mini_cfg(num_hidden_layers=4, max_position_embeddings=256)
+    w = make_decoder_weights(cfg, seed=86, head_std=0.2)
+    dcfg = tiny_dac_cfg(n_codebooks=cfg.num_codebooks, codebook_size=cfg.codebook_size)
+    B, S, P, steps = 32, 24, 12, 40     # cache length 13 -> 53: several 16-key ring chunks per attention warp
+    enc, enc_mask, prompt, prompt_mask = synth_inputs(cfg, B, S, P, seed=15)
+    L = steps + 2
+    out = {}
+    forced = None
+    for mode in ("legacy", "cluster"):
+        monkeypatch.setenv("PTTS_STEP", mode)
+        model = build_product_model(cfg, dcfg, w, make_dac_weights(dcfg, seed=1), dtype=torch.bfloat16)
+        sess = model.decoder.engine.session(B, P, S, P + L)
+        sess.begin(L, do_sample=False)
+        sess.prefill(prompt.to(DEV), prompt_mask, enc.to(DEV), enc_mask)
+        assert sess.fused == (1 if mode == "legacy" else 2), (mode, sess.fused)
+        logits, toks = [], []
+        for t in range(steps):
+            if t > 0:
+                sess.decode_forward()
+                logits.append(sess.logits.float().cpu().numpy().copy())
+            sess.sample(forced=None if forced is None else torch.from_numpy(forced[:, t].copy()))
+            toks.append(sess.raw_ids[:, t + 1].cpu().numpy().copy())
+        torch.cuda.synchronize()
+        out[mode] = (np.stack(logits), np.stack(toks, 1))
+        if forced is None:
+            forced = out[mode][1]
+    a, b = out["cluster"][0], out["legacy"][0]
+    scale = np.abs(b).max()
+    assert np.isfinite(a).all()
+    err = np.abs(a - b).max(axis=(1, 2)) / scale
+    assert err.max() < 0.02, err
+    srt = np.sort(b, -1)
+    clear = (srt[..., -1] - srt[..., -2]) > 0.04 * scale
+    assert np.array_equal(a.argmax(-1)[clear], b.argmax(-1)[clear])
+    # free-running with the in-kernel sampler: runs to the end and stays finite
+    monkeypatch.setenv("PTTS_STEP", "cluster")
+    ids, lg, launches = _free_run_cluster(cfg, w, B, S, P, L, dict(do_sample=True, top_k=50, seed=5, min_new_tokens=L - 1, suppress_special=True, codebook_size=1024))
+    assert ids.shape[1] == L and np.isfinite(lg).all() and (ids[:, 1:] < 1024).all()
+
+
+def _free_run_cluster(cfg, w, B, S, P, L, gen):
+    dcfg = tiny_dac_cfg(n_codebooks=cfg.num_codebooks, codebook_size=cfg.codebook_size)
+    model = build_product_model(cfg, dcfg, w, make_dac_weights(dcfg, seed=1), dtype=torch.bfloat16)
+    enc, enc_mask, prompt, prompt_mask = synth_inputs(cfg, B, S, P, seed=3)
+    sess = model.decoder.engine.session(B, P, S, P + L)
+    sess.begin(L, **gen)
+    sess.prefill(prompt.to(DEV), prompt_mask, enc.to(DEV), enc_mask)
+    assert sess.fused == 2
+    sess.sample()
+    sess.decode_steps(L - 2)
+    torch.cuda.synchronize()
+    n = int(sess.state[0].item())
+    return sess.raw_ids[:, :n].cpu().numpy().copy(), sess.logits.cpu().numpy().copy(), sess.launches
 
 
 def test_dac_decode_real_shape_bf16_tensor_core(monkeypatch):
