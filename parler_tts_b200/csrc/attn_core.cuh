@@ -64,10 +64,10 @@ __device__ __forceinline__ void attention_item(const AttnArgs& p, int b, int kvh
           const float xp = DT<T>::to_f(src[d < HD / 2 ? d + HD / 2 : d - HD / 2]);
           x = rope_elem<T>(x, xp, d, rope_cos + (size_t)pos * HD, rope_sin + (size_t)pos * HD);
         }
-        kc[(size_t)pos * p.kv_t_stride + d] = DT<T>::from_f(x);
+        kc[(size_t)pos * p.kv_t_stride + kv_swz(pos, d)] = DT<T>::from_f(x);
       } else {
         const T* src = reinterpret_cast<const T*>(p.vnew) + r * p.ldkv + p.v_col0 + kvh * HD;
-        vc[(size_t)pos * p.kv_t_stride + d] = src[d];
+        vc[(size_t)pos * p.kv_t_stride + kv_swz(pos, d)] = src[d];
       }
     }
     sync();  // this CTA is the only reader of the rows it just wrote
@@ -108,7 +108,7 @@ __device__ __forceinline__ void attention_item(const AttnArgs& p, int b, int kvh
         for (int u = 0; u < 4; u++) {
           const int t = t0 + u * 16 + kslot;
           ok[u] = t < T_keys;
-          if (ok[u]) load8(kc + (size_t)t * p.kv_t_stride + d0, kv[u]);
+          if (ok[u]) load8(kc + (size_t)t * p.kv_t_stride + kv_swz(t, d0), kv[u]);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -150,7 +150,7 @@ __device__ __forceinline__ void attention_item(const AttnArgs& p, int b, int kvh
           const int t = t0 + u * 16 + kslot;
           pw[u] = 0.f;
           if (t < T_keys) {
-            load8(vc + (size_t)t * p.kv_t_stride + d0, vv[u]);
+            load8(vc + (size_t)t * p.kv_t_stride + kv_swz(t, d0), vv[u]);
             pw[u] = DT<T>::rnd(sc[t]);
           } else {
 #pragma unroll
@@ -274,10 +274,10 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
       x0 = y0; x1 = y1;
     }
     const T v0 = vsrc[lo], v1 = vsrc[hi];
-    kc[(size_t)pos * p.kv_t_stride + lo] = DT<T>::from_f(x0);
-    kc[(size_t)pos * p.kv_t_stride + hi] = DT<T>::from_f(x1);
-    vc[(size_t)pos * p.kv_t_stride + lo] = v0;
-    vc[(size_t)pos * p.kv_t_stride + hi] = v1;
+    kc[(size_t)pos * p.kv_t_stride + kv_swz(pos, lo)] = DT<T>::from_f(x0);
+    kc[(size_t)pos * p.kv_t_stride + kv_swz(pos, hi)] = DT<T>::from_f(x1);
+    vc[(size_t)pos * p.kv_t_stride + kv_swz(pos, lo)] = v0;
+    vc[(size_t)pos * p.kv_t_stride + kv_swz(pos, hi)] = v1;
     kn[lo] = DT<T>::rnd(x0); kn[hi] = DT<T>::rnd(x1);
     vn[lo] = DT<T>::to_f(v0); vn[hi] = DT<T>::to_f(v1);
   }
@@ -316,7 +316,7 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
       for (int u = 0; u < PER; u++) {
         const int r = u * 4 + grp, rc = r < n ? r : n - 1;
         float kf[8];
-        load8(kb + rc * HD + d0, kf);
+        load8(kb + rc * HD + kv_swz(rc, d0), kf);   // (stages start at multiples of 8 keys: t & 7 == rc & 7)
         float s = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; e++) s = fmaf(qv[e], kf[e], s);
@@ -350,7 +350,7 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
         lsum += pe;  // identical on the 8 lanes of the group; counted once below
         const float pw = DT<T>::rnd(pe);
         float vf[8];
-        load8(vb + rc * HD + d0, vf);
+        load8(vb + rc * HD + kv_swz(rc, d0), vf);
 #pragma unroll
         for (int e = 0; e < 8; e++) acc[e] = fmaf(pw, vf[e], acc[e]);
       }
@@ -442,6 +442,254 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
       for (int e = 0; e < 8; e++) o[e] = acc[e] * inv;
       store8(reinterpret_cast<T*>(p.out) + (size_t)b * p.ldo + h * HD + d0, o);
     }
+  }
+}
+
+// ---- decode attention on the tensor cores (bf16, MHA: one query head per K/V head) -----------------------------------------
+// Same contract, ring and merge protocol as attention_decode_item_warp, but a 16-key stage costs 16 mma.m16n8k16 instead of
+// ~250 scalar instructions (the SIMT sweep measured 37 ns per key per warp, latency-bound: profiles/r02_step2_phases.md):
+//   S = q K^T : A = the query in row 0 of an m16 x k16 fragment (4 k-steps over the 64 dims; rows 1..15 are zero),
+//               B = K rows straight from the staged tile with ldmatrix (keys are the n dimension) -> 2 n-tiles x 4 k-steps = 8 MMAs;
+//   O += P V  : A = the probabilities, which already sit in the A-fragment registers after the S MMAs (row 0 of the C fragment
+//               of n-tile 0 / 1 = columns 0-7 / 8-15 of the A fragment), B = V rows with ldmatrix.trans -> 8 n-tiles = 8 MMAs.
+// The K/V rows are stored swizzled (kv_swz, common.cuh), so the contiguous bulk copy of a stage is a conflict-free ldmatrix tile.
+// Only lanes 0..3 (fragment row 0) carry softmax state; fp32 scores / running max / sum, probabilities rounded to bf16 before
+// P V like the SIMT path and torch's flash kernels.
+__device__ __forceinline__ void att_ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void att_ldsm4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void att_mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t att_pack(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+constexpr int ATT_TC_CH = 16;   // keys per ring stage
+__host__ __device__ constexpr int attn_decode_tc_smem_per_warp() { return 2 * 2 * ATT_TC_CH * HD * 2 + (3 * HD) * (int)sizeof(float); }
+
+// sm_warp must be 1024-byte aligned relative to nothing in particular (ldmatrix needs 16 B); bars: this warp's two mbarriers.
+__device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p, int b, int h, int pos, unsigned char* sm_warp, uint64_t* bars,
+                                                              int lane, uint32_t& parity, int part, int nparts, float* xch, int pair_bar) {
+  constexpr int CH = ATT_TC_CH;
+  constexpr int STAGE_ELEMS = CH * HD;
+  bf16* kst = reinterpret_cast<bf16*>(sm_warp);                 // [2][CH][64] swizzled rows
+  bf16* vst = kst + 2 * STAGE_ELEMS;
+  float* qs = reinterpret_cast<float*>(vst + 2 * STAGE_ELEMS);   // [64] query (fp32 of the bf16 values)
+  float* kn = qs + HD;                                           // [64] this step's key   (self only)
+  float* vn = kn + HD;                                           // [64] this step's value (self only)
+  const bf16* __restrict__ rope_cos = reinterpret_cast<const bf16*>(p.rope_cos) + (size_t)pos * HD;
+  const bf16* __restrict__ rope_sin = reinterpret_cast<const bf16*>(p.rope_sin) + (size_t)pos * HD;
+  bf16* kc = reinterpret_cast<bf16*>(p.kcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
+  bf16* vc = reinterpret_cast<bf16*>(p.vcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
+  const int lo = lane, hi = lane + HD / 2;
+  const int n_cached = p.cross ? p.kv_len : pos;
+  const int n_chunks_all = (n_cached + CH - 1) / CH;
+  const int n_chunks = (n_chunks_all > part) ? (n_chunks_all - part + nparts - 1) / nparts : 0;
+
+  auto issue = [&](int i) {
+    const int st = i & 1;
+    const int t0 = (part + nparts * i) * CH;
+    const int n = (n_cached - t0 < CH) ? (n_cached - t0) : CH;
+    const uint32_t bar = att_smem_u32(&bars[st]);
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * n * HD * 2)) : "memory");
+    __syncwarp();
+    if (lane < 2) {
+      const bf16* src = (lane == 0 ? kc : vc) + (size_t)t0 * HD;
+      bf16* dst = (lane == 0 ? kst : vst) + st * STAGE_ELEMS;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(att_smem_u32(dst)), "l"(src), "r"((uint32_t)(n * HD * 2)), "r"(bar) : "memory");
+    }
+  };
+  auto wait_stage = [&](int st) {
+    const uint32_t bar = att_smem_u32(&bars[st]);
+    const uint32_t par = (parity >> st) & 1u;
+    uint32_t ok, spins = 0;
+    do {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(par) : "memory");
+      if (!ok && ++spins > (1u << 16)) { if (lane == 0) printf("ptts: tc attention KV mbarrier timeout (cta %d b %d h %d stage %d cross %d n_cached %d)\n", (int)blockIdx.x, b, h, st, p.cross, n_cached); __trap(); }
+    } while (!ok);
+    parity ^= (1u << st);
+  };
+
+  __syncwarp();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (n_chunks > 0) issue(0);
+  if (n_chunks > 1) issue(1);
+
+  // query (+ rotary), this step's K/V row (self): to the cache and to shared memory
+  {
+    const bf16* qsrc = reinterpret_cast<const bf16*>(p.q) + (size_t)b * p.ldq + p.q_col0 + (size_t)h * HD;
+    float x0 = __bfloat162float(qsrc[lo]), x1 = __bfloat162float(qsrc[hi]);
+    if (p.rope) {
+      const float y0 = rope_elem<bf16>(x0, x1, lo, rope_cos, rope_sin), y1 = rope_elem<bf16>(x1, x0, hi, rope_cos, rope_sin);
+      x0 = y0; x1 = y1;
+    }
+    qs[lo] = x0; qs[hi] = x1;
+  }
+  if (!p.cross && part == 0) {
+    const bf16* ksrc = reinterpret_cast<const bf16*>(p.knew) + (size_t)b * p.ldkv + p.k_col0 + h * HD;
+    const bf16* vsrc = reinterpret_cast<const bf16*>(p.vnew) + (size_t)b * p.ldkv + p.v_col0 + h * HD;
+    float x0 = __bfloat162float(ksrc[lo]), x1 = __bfloat162float(ksrc[hi]);
+    if (p.rope) {
+      const float y0 = rope_elem<bf16>(x0, x1, lo, rope_cos, rope_sin), y1 = rope_elem<bf16>(x1, x0, hi, rope_cos, rope_sin);
+      x0 = y0; x1 = y1;
+    }
+    const bf16 v0 = vsrc[lo], v1 = vsrc[hi];
+    kc[(size_t)pos * p.kv_t_stride + kv_swz(pos, lo)] = __float2bfloat16_rn(x0);
+    kc[(size_t)pos * p.kv_t_stride + kv_swz(pos, hi)] = __float2bfloat16_rn(x1);
+    vc[(size_t)pos * p.kv_t_stride + kv_swz(pos, lo)] = v0;
+    vc[(size_t)pos * p.kv_t_stride + kv_swz(pos, hi)] = v1;
+    kn[lo] = DT<bf16>::rnd(x0); kn[hi] = DT<bf16>::rnd(x1);
+    vn[lo] = __bfloat162float(v0); vn[hi] = __bfloat162float(v1);
+  }
+  __syncwarp();
+  const int g = lane >> 2, t = lane & 3;
+  // A fragments of the query: row 0 only (lanes 0..3): k-step ks covers dims 16 ks .. 16 ks + 15
+  uint32_t qa0[4], qa2[4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++) {
+    qa0[ks] = (g == 0) ? att_pack(qs[16 * ks + 2 * t], qs[16 * ks + 2 * t + 1]) : 0u;
+    qa2[ks] = (g == 0) ? att_pack(qs[16 * ks + 8 + 2 * t], qs[16 * ks + 8 + 2 * t + 1]) : 0u;
+  }
+  const int* km = p.key_mask ? p.key_mask + (size_t)b * p.mask_ld : nullptr;
+  float m_run = -INFINITY, l_run = 0.f;
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) o[j][e] = 0.f;
+  // ldmatrix lane addressing inside a stage: matrix mi = lane >> 3, row r = lane & 7 (16-byte chunk c of key row k at (c ^ (k & 7)) * 16)
+  const int mi = lane >> 3, r8 = lane & 7;
+
+  for (int c = 0; c < n_chunks; c++) {
+    const int st = c & 1;
+    const int t0 = (part + nparts * c) * CH;
+    const int n = (n_cached - t0 < CH) ? (n_cached - t0) : CH;
+    int mk = 1;
+    if (km != nullptr && lane < CH && t0 + lane < p.mask_len && t0 + lane < n_cached) mk = km[t0 + lane];
+    wait_stage(st);
+    const uint32_t mword = __ballot_sync(0xffffffffu, mk != 0);
+    const uint32_t kbase = att_smem_u32(kst + st * STAGE_ELEMS), vbase = att_smem_u32(vst + st * STAGE_ELEMS);
+    if (n < CH) {  // last, partial stage: the copy filled n rows; whatever the rest of the V stage holds must not meet the MMA
+      // (probability 0 x a stale NaN bit pattern is NaN); stale K rows only produce scores that are replaced by -inf below
+      for (int i = lane; i < (CH - n) * 8; i += 32)
+        *reinterpret_cast<uint4*>(vst + st * STAGE_ELEMS + (size_t)(n + (i >> 3)) * HD + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
+      __syncwarp();
+    }
+    // ---- scores of the 16 keys ----
+    float s[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) s[nt][e] = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {   // chunks 4 half .. 4 half + 3 of the key rows = k-steps 2 half, 2 half + 1
+        uint32_t kb[4];
+        att_ldsm4(kb, kbase + (uint32_t)((8 * nt + r8) * 128 + (((4 * half + mi) ^ r8) << 4)));
+        att_mma(s[nt], qa0[2 * half], 0u, qa2[2 * half], 0u, kb[0], kb[1]);
+        att_mma(s[nt], qa0[2 * half + 1], 0u, qa2[2 * half + 1], 0u, kb[2], kb[3]);
+      }
+    }
+    // lanes 0..3 (g == 0): s[nt][0], s[nt][1] = keys 8 nt + 2 t, 8 nt + 2 t + 1
+    float sv[4];
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int key = 8 * nt + 2 * t + e;
+        sv[2 * nt + e] = (g == 0 && key < n && ((mword >> key) & 1u)) ? s[nt][e] * p.scale : -INFINITY;
+      }
+    float cmax = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
+    cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 1));
+    cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 2));
+    cmax = __shfl_sync(0xffffffffu, cmax, 0);          // the g == 0 quad's maximum, warp-uniform
+    const float m_new = fmaxf(m_run, cmax);
+    if (m_new != -INFINITY) {                          // (warp-uniform) otherwise every key so far is masked
+      const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
+      float pe[4], lsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; i++) { pe[i] = expf(sv[i] - m_new); lsum += pe[i]; }   // exactly 0 for masked / out-of-range keys and lanes >= 4
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+      l_run = l_run * corr + lsum;                     // meaningful on lanes 0..3
+      m_run = m_new;
+      const uint32_t pa0 = att_pack(pe[0], pe[1]), pa2 = att_pack(pe[2], pe[3]);   // probabilities rounded to bf16 (zeros off row 0)
+#pragma unroll
+      for (int j = 0; j < 8; j++) { o[j][0] *= corr; o[j][1] *= corr; }
+#pragma unroll
+      for (int jp = 0; jp < 4; jp++) {                 // dims 16 jp .. 16 jp + 15: n-tiles 2 jp, 2 jp + 1
+        uint32_t vb[4];
+        // matrices: (n-tile 2jp, keys 0-7), (2jp, keys 8-15), (2jp+1, keys 0-7), (2jp+1, keys 8-15); rows = keys, transposed on load
+        const int key = (mi & 1) * 8 + r8, chunk = 2 * jp + (mi >> 1);
+        att_ldsm4_t(vb, vbase + (uint32_t)(key * 128 + ((chunk ^ r8) << 4)));
+        att_mma(o[2 * jp], pa0, 0u, pa2, 0u, vb[0], vb[1]);
+        att_mma(o[2 * jp + 1], pa0, 0u, pa2, 0u, vb[2], vb[3]);
+      }
+    }
+    if (c + 2 < n_chunks) {
+      __syncwarp();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(c + 2);
+    }
+  }
+  // lanes 0..3 hold the output row: o[j][0], o[j][1] = dims 8 j + 2 t, 8 j + 2 t + 1
+  if (!p.cross && part == 0) {  // the step's own key (position `pos`), from shared memory
+    float sdot = 0.f;
+#pragma unroll
+    for (int e = 0; e < 2; e++) sdot = fmaf(qs[lane * 2 + e], kn[lane * 2 + e], sdot);
+    sdot = warp_sum(sdot) * p.scale;
+    if (km != nullptr && pos < p.mask_len && km[pos] == 0) sdot = -INFINITY;
+    const float m_new = fmaxf(m_run, sdot);
+    if (m_new != -INFINITY) {
+      const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
+      const float pe = (sdot == -INFINITY) ? 0.f : expf(sdot - m_new);
+      const float pw = DT<bf16>::rnd(pe);
+      l_run = l_run * corr + pe;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        o[j][0] = o[j][0] * corr + pw * vn[8 * j + 2 * t];
+        o[j][1] = o[j][1] * corr + pw * vn[8 * j + 2 * t + 1];
+      }
+      m_run = m_new;
+    }
+  }
+  if (nparts == 2) {  // merge the two warps' partial softmax states (fixed order: part 0 then part 1)
+    if (part == 1) {
+      if (lane < 4) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { xch[8 * j + 2 * t] = o[j][0]; xch[8 * j + 2 * t + 1] = o[j][1]; }
+      }
+      if (lane == 0) { xch[HD] = m_run; xch[HD + 1] = l_run; }
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    if (part == 0) {
+      const float m1 = xch[HD], l1 = xch[HD + 1];
+      const float mm = fmaxf(m_run, m1);
+      const float c0 = (m_run == -INFINITY) ? 0.f : expf(m_run - mm);
+      const float c1 = (m1 == -INFINITY) ? 0.f : expf(m1 - mm);
+      l_run = l_run * c0 + l1 * c1;
+      if (lane < 4) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          o[j][0] = o[j][0] * c0 + xch[8 * j + 2 * t] * c1;
+          o[j][1] = o[j][1] * c0 + xch[8 * j + 2 * t + 1] * c1;
+        }
+      }
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+  }
+  if (lane < 4 && part == 0) {
+    const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;  // fully masked row -> zeros (never consumed)
+    bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)b * p.ldo + h * HD;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      *reinterpret_cast<__nv_bfloat162*>(out + 8 * j + 2 * t) = __floats2bfloat162_rn(o[j][0] * inv, o[j][1] * inv);
   }
 }
 

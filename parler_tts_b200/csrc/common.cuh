@@ -116,6 +116,12 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+// K/V cache rows are stored SWIZZLED: element d of the 64-wide row of key t lives at position kv_swz(t, d) -- the 8-element
+// (16-byte bf16) chunk index XORed with t & 7.  A contiguous bulk copy of 8n rows then lands in shared memory as a
+// bank-conflict-free ldmatrix tile (what a SWIZZLE_128B tensor map would produce) with no tensor map: the tensor-core attention
+// of the cluster step kernel depends on it, every other reader / writer of the caches just applies the same index map.
+__host__ __device__ __forceinline__ int kv_swz(int t, int d) { return ((((d >> 3) ^ t) & 7) << 3) | (d & 7); }
+
 // Programmatic dependent launch: everything before pdl_wait() overlaps the previous kernel's tail.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -88,7 +88,7 @@ __global__ void cross_kv_relayout_kernel(const T* __restrict__ src, T* __restric
     const int is_v = c >= nckv * 64;
     const int cc = c - is_v * nckv * 64;
     const int h = cc >> 6, d = cc & 63;
-    dst[(size_t)is_v * B * nckv * S * 64 + (((size_t)b * nckv + h) * S + sidx) * 64 + d] = src[(size_t)row * width + c];
+    dst[(size_t)is_v * B * nckv * S * 64 + (((size_t)b * nckv + h) * S + sidx) * 64 + kv_swz(sidx, d)] = src[(size_t)row * width + c];  // swizzled rows (common.cuh)
   }
 }
 int launch_cross_kv_relayout(const void* src, void* dst, int B, int S, int nckv, int dtype, cudaStream_t st) {

@@ -41,7 +41,7 @@ struct DecoderLayout {
 static inline bool cluster_shape_ok(const ptts_decoder_config& c) {
   const int H = c.hidden_size, nh = c.num_heads, F = c.ffn_dim;
   return c.dtype == PTTS_BF16 && c.num_kv_heads == nh && c.num_cross_kv_heads == nh && nh * 8 <= 144 && H == nh * PTTS_HEAD_DIM &&
-         H % 256 == 0 && F % 256 == 0 && F % (nh * 64) == 0 && F / (nh * 64) <= 4 && H <= 1024 && F <= 4096 && c.num_codebooks <= 16 &&
+         H % 256 == 0 && F % 256 == 0 && F % (nh * 64) == 0 && (F / (nh * 64) == 1 || F / (nh * 64) == 2 || F / (nh * 64) == 4) && H <= 1024 && F <= 4096 && c.num_codebooks <= 16 &&
          (c.vocab_size * c.num_codebooks) % 32 == 0;
 }
 

@@ -78,6 +78,13 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) { uint32_
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_f2(uint32_t addr, float a, float b) { asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory"); }
+__device__ __forceinline__ void st_cluster_f1(uint32_t addr, float a) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory"); }
+// arrive (release, cluster scope) on a peer's mbarrier: orders this thread's (and, through the preceding __syncwarp, its warp's)
+// remote stores before the receiver's acquire wait
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
   const char* c = reinterpret_cast<const char*>(p);
@@ -116,6 +123,62 @@ __device__ __forceinline__ unsigned grid_sync(unsigned* ctr, unsigned target, in
   }
   __syncthreads();
   return target;
+}
+
+// One warp's MMA loop: QN n-tiles x MT m-tiles over k-tiles [kt_lo, kt_hi) of the staged slice.  SETS independent accumulator
+// sets (k-tile parity x k16 half) break the dependent HMMA chain of the narrow phases (q = 1: out-proj, fc2 -- 32 dependent
+// MMAs at 16 k-tiles otherwise); they are summed in a fixed order at the end.  STATS: the warp also accumulates the LayerNorm
+// row sums of the k-tiles with (kt & 3) == dgrp from the A fragments it has loaded anyway.
+template <int QN, int MT, int SETS, bool STATS>
+__device__ __forceinline__ void mma_slice(float (&out)[2][6][4], RowStatFrag& rst, const bf16* xs, int apitch, const uint4* wb, int KT, int kt_lo,
+                                          int kt_hi, int dgrp, int lrow, int lcol) {
+  float acc[SETS][MT][QN][4];
+#pragma unroll
+  for (int s = 0; s < SETS; s++)
+#pragma unroll
+    for (int a = 0; a < MT; a++)
+#pragma unroll
+      for (int j = 0; j < QN; j++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) acc[s][a][j][e] = 0.f;
+  constexpr int KU = (SETS == 4) ? 2 : 1;   // k-tiles per iteration: the accumulator set index must be a compile-time constant
+  for (int kt0 = kt_lo; kt0 < kt_hi; kt0 += KU) {   // (kt_hi - kt_lo is even: half of a slice of 8 or 32 k-tiles)
+#pragma unroll
+    for (int u = 0; u < KU; u++) {
+      const int kt = kt0 + u;
+      uint32_t a[MT][2][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) ldsm4(a[mt][j], xs + (size_t)(mt * 16 + lrow) * apitch + kt * 32 + j * 16 + lcol);
+      if (STATS && (kt & 3) == dgrp) {
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) { row_stat_mma(rst, mt, a[mt][0]); row_stat_mma(rst, mt, a[mt][1]); }
+      }
+      constexpr int SB = (SETS >= 2) ? 1 : 0;
+      const int s0 = (SETS == 4) ? 2 * u : 0;   // u is an unrolled constant
+#pragma unroll
+      for (int j = 0; j < QN; j++) {
+        const uint4 w = wb[((size_t)j * KT + kt) * 32];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+          mma_bf16_16816(acc[s0][mt][j], a[mt][0], w.x, w.y);
+          mma_bf16_16816(acc[s0 + SB][mt][j], a[mt][1], w.z, w.w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+    for (int j = 0; j < QN; j++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        float v = acc[0][mt][j][e];
+#pragma unroll
+        for (int s2 = 1; s2 < SETS; s2++) v += acc[s2][mt][j][e];
+        out[mt][j][e] = v;
+      }
 }
 
 // phase kinds of a layer
@@ -175,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   uint32_t par_a = 0, par_w = 0, par_x = 0, att_parity = 0;
 
   if (tid == 0) {
-    mbar_init(abar, 1); mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1); mbar_init(xbar, 1);
+    mbar_init(abar, 1); mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1); mbar_init(xbar, V * C);   // xbar: one arrival per warp of the cluster
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   attention_decode_init_warp(attbars + 2 * warp, lane);
@@ -216,8 +279,24 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       l2_prefetch(k + vofs, (uint32_t)(n * HD * 2));
     }
   };
+  // the same requests cut into one piece per warp (issued by lane 0 of every warp: a prefetch is ~100 cycles of issue time)
+  auto prefetch_weight_job_part = [&](int j, int w) {
+    const char* src; uint32_t bytes;
+    if (weight_job(p, j, cta, rank, src, bytes)) { const uint32_t pc = (bytes / V) & ~15u; l2_prefetch(src + (size_t)w * pc, w == V - 1 ? bytes - (V - 1) * pc : pc); }
+  };
+  auto prefetch_kv_part = [&](int l, bool cross, int w) {  // warp w: item w >> 1, K (even w) or V (odd w)
+    const int T = cross ? p.S : p.Tmax, n = cross ? p.S : pos;
+    const int b = 16 * half + 4 * rank + (w >> 1);
+    if (n <= 0 || b >= B) return;
+    const char* kc = cross ? p.cross_kv + p.cross_layer_stride * l : p.self_kv + p.self_layer_stride * l;
+    const char* k = kc + ((size_t)b * p.nh + head) * T * HD * 2 + ((w & 1) ? (size_t)B * p.nh * T * HD * 2 : 0);
+    l2_prefetch(k, (uint32_t)(n * HD * 2));
+  };
   if (tid == 0) { issue_weight_job(0); issue_weight_job(1); }
-  if (tid == 64) { for (int j = 2; j < JOBS_PER_LAYER; j++) prefetch_weight_job(j); prefetch_kv(0, false); prefetch_kv(0, true); }
+  if (lane == 0) {
+    for (int j = 2; j < JOBS_PER_LAYER; j++) prefetch_weight_job_part(j, warp);
+    prefetch_kv_part(0, false, warp); prefetch_kv_part(0, true, warp);
+  }
 
   // global activation images, K-sliced for their consumer: [4 slices][32 rows][slice width + 8] bf16
   bf16* const x_img = p.cl_x;       // slices of H/4 columns (consumers: QKV, q_cross, fc1, lm heads)
@@ -286,9 +365,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     const int act_bytes = (rowpart ? 16 : ROWS) * apitch * 2;
     // exchange geometry: block (destination rank d, K half) at index 2 d + kh
     const int RS = (q == 1) ? 8 : 8 * q + 2;                         // floats per row of a feature-partitioned block
-    const int blk = rowpart ? (32 + 4 * Nc * 4) : (256 + ROWS * RS * 4);
-    unsigned char* send = Rg + ((act_bytes + 127) & ~127);
-    unsigned char* recv = send + ((V * blk + 127) & ~127);
+    const int blk = rowpart ? 4 * Nc * 4 : ROWS * RS * 4;            // one (source rank, K half) accumulator slot of this CTA
     const int j0 = JOBS_PER_LAYER * l + (sub == 0 ? 0 : sub + 1);    // first weight job of this phase
     const int njobs = sub == 0 ? 2 : 1;
 
@@ -318,12 +395,6 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     par_a ^= 1u;
     prof_mark(prof, 1);
     float acc[2][QMAX][4];
-#pragma unroll
-    for (int a = 0; a < 2; a++)
-#pragma unroll
-      for (int j = 0; j < QMAX; j++)
-#pragma unroll
-        for (int e = 0; e < 4; e++) acc[a][j][e] = 0.f;
     RowStatFrag rst;
     row_stat_zero(rst);
     {
@@ -333,101 +404,90 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       const int nt0 = (sub == PH_QKV) ? (dgrp & 1) * q : dgrp * q;   // first n-tile of this warp inside that job's slice
       const uint4* wb = reinterpret_cast<const uint4*>(smem + HDR + (wjob & 1) * WB_BYTES) + (size_t)nt0 * KT * 32 + lane;
       const int kt_lo = kh * (KT >> 1), kt_hi = kt_lo + (KT >> 1);
-      for (int kt = kt_lo; kt < kt_hi; kt++) {
-        uint32_t a[2][2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++)
-          if (mt < MT) {
-#pragma unroll
-            for (int j = 0; j < 2; j++) ldsm4(a[mt][j], xs + (size_t)(mt * 16 + lrow) * apitch + kt * 32 + j * 16 + lcol);
-          }
-        if (has_ln && (kt & 3) == dgrp) {  // row statistics of k-tile kt ride on the fragments already loaded (one warp per k-tile)
-#pragma unroll
-          for (int mt = 0; mt < 2; mt++)
-            if (mt < MT) { row_stat_mma(rst, mt, a[mt][0]); row_stat_mma(rst, mt, a[mt][1]); }
-        }
-#pragma unroll
-        for (int j = 0; j < QMAX; j++) {
-          if (j < q) {
-            const uint4 w = wb[((size_t)j * KT + kt) * 32];
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-              if (mt < MT) {
-                mma_bf16_16816(acc[mt][j], a[mt][0], w.x, w.y);
-                mma_bf16_16816(acc[mt][j], a[mt][1], w.z, w.w);
-              }
-          }
-        }
-      }
+      if (sub == PH_QKV) mma_slice<6, 1, 1, true>(acc, rst, xs, apitch, wb, KT, kt_lo, kt_hi, dgrp, lrow, lcol);
+      else if (sub == PH_QC) mma_slice<2, 1, 4, true>(acc, rst, xs, apitch, wb, KT, kt_lo, kt_hi, dgrp, lrow, lcol);
+      else if (sub == PH_FC1) {
+        if (q == 4) mma_slice<4, 2, 1, true>(acc, rst, xs, apitch, wb, KT, kt_lo, kt_hi, dgrp, lrow, lcol);
+        else if (q == 2) mma_slice<2, 2, 2, true>(acc, rst, xs, apitch, wb, KT, kt_lo, kt_hi, dgrp, lrow, lcol);
+        else mma_slice<1, 2, 4, true>(acc, rst, xs, apitch, wb, KT, kt_lo, kt_hi, dgrp, lrow, lcol);
+      } else mma_slice<1, 2, 4, false>(acc, rst, xs, apitch, wb, KT, kt_lo, kt_hi, dgrp, lrow, lcol);
     }
     prof_mark(prof, 2);
     __syncthreads();  // activation slice and weight buffer(s) are dead
-    if (tid == 32) {  // refill the ring two jobs ahead; pull the same jobs of the next layer (or the lm heads) into L2
-      for (int i = 0; i < njobs; i++) { issue_weight_job(j0 + i + 2); prefetch_weight_job(j0 + i + JOBS_PER_LAYER); }
-      if (sub == PH_O && l + 1 < p.L) prefetch_kv(l + 1, false);
-      if (sub == PH_OC && l + 1 < p.L) prefetch_kv(l + 1, true);
+    if (lane == 0) {  // asynchronous requests, one or two per warp so that no single thread holds the CTA back
+      if (warp == 1) for (int i = 0; i < njobs; i++) issue_weight_job(j0 + i + 2);   // refill the ring two jobs ahead
+      for (int i = 0; i < njobs; i++) prefetch_weight_job_part(j0 + i + JOBS_PER_LAYER, warp);  // same job, next layer (or lm heads) -> L2
+      if (sub == PH_O && l + 1 < p.L) prefetch_kv_part(l + 1, false, warp);
+      if (sub == PH_OC && l + 1 < p.L) prefetch_kv_part(l + 1, true, warp);
     }
-    cluster_wait();  // every peer is past its previous exchange: my send blocks have been read, its receive slots are free
+    cluster_wait();  // every peer is past its previous epilogue: its receive slots are free
 
-    // ---- partial sums -> send blocks ----
-    if (has_ln) row_stat_store(rst, part, warp, lane);   // (for MT == 1 the second m-tile's entries are zero and never read)
-    if (!rowpart) {   // block (dgrp, kh) = [stats 32x2][32 rows][RS]: what rank dgrp finalises, this K half's share
-      float* blkp = reinterpret_cast<float*>(send + (size_t)(2 * dgrp + kh) * blk + 256);
+    // ---- partial sums straight into the destination ranks' receive slots (DSMEM stores from registers) ----
+    // accumulator slot v = 2 src_rank + K half; statistics slot = 8 src_rank + warp
+    const uint32_t recv_acc = s32(Rg) + (uint32_t)((act_bytes + 127) & ~127);
+    const uint32_t recv_st = recv_acc + (uint32_t)((V * blk + 127) & ~127);
+    const int stb = rowpart ? 32 : 256;   // bytes of one statistics slot: (S1, S2) of 4 / 32 rows
+    {
+      const uint32_t my_slot = recv_acc + (uint32_t)((2 * rank + kh) * blk);
+      if (!rowpart) {   // block [32 rows][RS]: everything rank dgrp finalises, this warp's K half
+        const uint32_t dst = mapa(my_slot, (uint32_t)dgrp);
 #pragma unroll
-      for (int mt = 0; mt < 2; mt++)
+        for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-        for (int j = 0; j < QMAX; j++) {
-          if (j < q) {
-            float* base = blkp + (size_t)(mt * 16 + g) * RS + j * 8 + 2 * t4;
-            *reinterpret_cast<float2*>(base) = make_float2(acc[mt][j][0], acc[mt][j][1]);
-            *reinterpret_cast<float2*>(base + 8 * RS) = make_float2(acc[mt][j][2], acc[mt][j][3]);
+          for (int j = 0; j < QMAX; j++) {
+            if (j < q) {
+              const uint32_t o = dst + (uint32_t)(((mt * 16 + g) * RS + j * 8 + 2 * t4) * 4);
+              st_cluster_f2(o, acc[mt][j][0], acc[mt][j][1]);
+              st_cluster_f2(o + (uint32_t)(8 * RS * 4), acc[mt][j][2], acc[mt][j][3]);
+            }
           }
+      } else {          // block [4 rows][Nc] per destination: rows 4d..4d+3 of this cluster's half, all of the head's features
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          const int row = g + 8 * hh;
+          const uint32_t dst = mapa(my_slot, (uint32_t)(row >> 2)) + (uint32_t)(((row & 3) * Nc + dgrp * q * 8 + 2 * t4) * 4);
+#pragma unroll
+          for (int j = 0; j < QMAX; j++)
+            if (j < q) st_cluster_f2(dst + (uint32_t)(j * 32), acc[0][j][2 * hh], acc[0][j][2 * hh + 1]);
         }
-    } else {          // block (d, kh) = [stats 4x2][4 rows][Nc]: rows 4d..4d+3 of this cluster's half, all of the head's features
+      }
+      if (has_ln) {   // this warp's LayerNorm partial sums (one k-tile) of rows g / g+8 of each m-tile (lane layout: ln_stats.cuh)
+        const uint32_t my_st = recv_st + (uint32_t)((8 * rank + warp) * stb);
 #pragma unroll
-      for (int j = 0; j < QMAX; j++) {
-        if (j < q) {
+        for (int mt = 0; mt < 2; mt++) {
+          if (mt < MT) {
+            const float s1a = rst.s1[mt][0], s1b = rst.s1[mt][2];
+            const float s2a = (g & 1) ? rst.sq[mt][0][1] : rst.sq[mt][0][0], s2b = (g & 1) ? rst.sq[mt][1][3] : rst.sq[mt][1][2];
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+            if (!rowpart) {
 #pragma unroll
-          for (int hh = 0; hh < 2; hh++) {
-            const int row = g + 8 * hh, col = (dgrp * q + j) * 8 + 2 * t4;
-            float* dst = reinterpret_cast<float*>(send + (size_t)(2 * (row >> 2) + kh) * blk + 32) + (row & 3) * Nc + col;
-            *reinterpret_cast<float2*>(dst) = make_float2(acc[0][j][2 * hh], acc[0][j][2 * hh + 1]);
+              for (int d = 0; d < C; d++) {
+                const uint32_t base = mapa(my_st, (uint32_t)d);
+                if (t4 == 0) { st_cluster_f1(base + r0 * 8, s1a); st_cluster_f1(base + r1 * 8, s1b); }
+                if (t4 == (g >> 1)) { st_cluster_f1(base + r0 * 8 + 4, s2a); st_cluster_f1(base + r1 * 8 + 4, s2b); }
+              }
+            } else {
+              const uint32_t b0 = mapa(my_st, (uint32_t)(r0 >> 2)) + (uint32_t)((r0 & 3) * 8), b1 = mapa(my_st, (uint32_t)(r1 >> 2)) + (uint32_t)((r1 & 3) * 8);
+              if (t4 == 0) { st_cluster_f1(b0, s1a); st_cluster_f1(b1, s1b); }
+              if (t4 == (g >> 1)) { st_cluster_f1(b0 + 4, s2a); st_cluster_f1(b1 + 4, s2b); }
+            }
           }
         }
       }
+      __syncwarp();
+      if (lane < C) mbar_arrive_cluster(mapa(s32(xbar), (uint32_t)lane));   // one arrival per (warp, destination): 32 per CTA per phase
     }
-    __syncthreads();
-    if (has_ln && tid < ROWS) {  // this CTA's partial (S1, S2) of row tid over its K slice: into the kh = 0 block headers (0 in kh = 1)
-      float S1 = 0.f, S2 = 0.f;
-#pragma unroll
-      for (int w = 0; w < V; w++) { S1 += part[((size_t)w * 32 + tid) * 2]; S2 += part[((size_t)w * 32 + tid) * 2 + 1]; }
-      if (!rowpart) {
-#pragma unroll
-        for (int d = 0; d < C; d++) {
-          *reinterpret_cast<float2*>(send + (size_t)(2 * d) * blk + tid * 8) = make_float2(S1, S2);
-          *reinterpret_cast<float2*>(send + (size_t)(2 * d + 1) * blk + tid * 8) = make_float2(0.f, 0.f);
-        }
-      } else if (tid < 16) {
-        *reinterpret_cast<float2*>(send + (size_t)(2 * (tid >> 2)) * blk + (tid & 3) * 8) = make_float2(S1, S2);
-        *reinterpret_cast<float2*>(send + (size_t)(2 * (tid >> 2) + 1) * blk + (tid & 3) * 8) = make_float2(0.f, 0.f);
-      }
-    }
-    __syncthreads();
-    if (tid < C && tid != rank) {  // one DSMEM bulk copy per peer: both K-half blocks for rank `tid` -> its receive slots [2 rank, 2 rank + 1]
-      fence_proxy_async_smem();
-      bulk_s2peer(mapa(s32(recv + (size_t)(2 * rank) * blk), (uint32_t)tid), send + (size_t)(2 * tid) * blk, (uint32_t)(2 * blk), mapa(s32(xbar), (uint32_t)tid));
-    }
-    if (tid == C) mbar_expect_tx(xbar, (uint32_t)((C - 1) * 2 * blk));
     mbar_wait(xbar, par_x, 2);
     par_x ^= 1u;
     prof_mark(prof, 3);
 
     // ---- epilogue: sum the 8 partial blocks in virtual-rank order, LayerNorm fix-up, activation / residual ----
-    auto block_of = [&](int v) -> const unsigned char* { return ((v >> 1) == rank) ? send + (size_t)v * blk : recv + (size_t)v * blk; };
+    const unsigned char* racc = Rg + ((act_bytes + 127) & ~127);
+    const unsigned char* rst_s = racc + ((V * blk + 127) & ~127);
     if (!rowpart) {
       if (has_ln && tid < ROWS) {
         float S1 = 0.f, S2 = 0.f;
-        for (int v = 0; v < V; v++) { const float2 x = *reinterpret_cast<const float2*>(block_of(v) + tid * 8); S1 += x.x; S2 += x.y; }
+        for (int v = 0; v < V * C; v++) { const float2 x = *reinterpret_cast<const float2*>(rst_s + (size_t)v * stb + tid * 8); S1 += x.x; S2 += x.y; }
         const float mean = S1 / (float)H;
         stats[2 * tid] = mean;
         stats[2 * tid + 1] = rsqrtf(fmaxf(S2 / (float)H - mean * mean, 0.f) + p.eps);
@@ -439,7 +499,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
           const int f = f0 + 8 * i;
           float v = 0.f;
 #pragma unroll
-          for (int s = 0; s < V; s++) v += reinterpret_cast<const float*>(block_of(s) + 256)[row * RS + f];
+          for (int sv = 0; sv < V; sv++) v += reinterpret_cast<const float*>(racc + (size_t)sv * blk)[row * RS + f];
           if (sub == PH_FC1) {
             v = stats[2 * row + 1] * (v - stats[2 * row] * cvec[f]) + cvec[256 + f];
             v = apply_act(DT<bf16>::rnd(v), p.act);
@@ -455,7 +515,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     } else {
       if (tid < 4) {  // rows 16 half + 4 rank + tid
         float S1 = 0.f, S2 = 0.f;
-        for (int v = 0; v < V; v++) { const float2 x = *reinterpret_cast<const float2*>(block_of(v) + tid * 8); S1 += x.x; S2 += x.y; }
+        for (int v = 0; v < V * C; v++) { const float2 x = *reinterpret_cast<const float2*>(rst_s + (size_t)v * stb + tid * 8); S1 += x.x; S2 += x.y; }
         const float mean = S1 / (float)H;
         stats[2 * tid] = mean;
         stats[2 * tid + 1] = rsqrtf(fmaxf(S2 / (float)H - mean * mean, 0.f) + p.eps);
@@ -466,19 +526,14 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         const int r4 = idx / Nc, col = idx - r4 * Nc;
         float v = 0.f;
 #pragma unroll
-        for (int s = 0; s < V; s++) v += reinterpret_cast<const float*>(block_of(s) + 32)[r4 * Nc + col];
+        for (int sv = 0; sv < V; sv++) v += reinterpret_cast<const float*>(racc + (size_t)sv * blk)[r4 * Nc + col];
         v = stats[2 * r4 + 1] * (v - stats[2 * r4] * cvec[col]) + cvec[256 + col];
         qkv_s[idx] = __float2bfloat16_rn(v);
       }
     }
     prof_mark(prof, 4);
-    __syncthreads();   // receive slots and this CTA's reads of its own send blocks are done (and q|k|v complete)
+    __syncthreads();   // this CTA's receive slots are consumed (and q|k|v complete): peers may write the next phase's partials
     cluster_arrive();
-    if (rowpart) {
-      // attention scratch aliases the send blocks: the peers must have RECEIVED them (each is past its exchange wait) first
-      cluster_wait();
-      cluster_arrive();  // re-arm for the next phase's "exchange buffers free" wait
-    }
 
     // ---- attention of this rank's 4 (row, head) items: two warps per item ----
     if (rowpart) {
@@ -511,9 +566,12 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       }
       const int pair = warp >> 1, part_i = warp & 1;
       const int b = row_base + pair;
-      unsigned char* region = Rg + (size_t)warp * attn_decode_smem_per_warp<bf16, ATT_CH>();
-      float* xch = reinterpret_cast<float*>(Rg + (size_t)V * attn_decode_smem_per_warp<bf16, ATT_CH>()) + pair * 128;
-      if (b < B) attention_decode_item_warp<bf16, ATT_CH>(a, b, head, pos, region, attbars + 2 * warp, lane, att_parity, part_i, 2, xch, pair + 1);
+      unsigned char* region = Rg + (size_t)warp * attn_decode_tc_smem_per_warp();
+      float* xch = reinterpret_cast<float*>(Rg + (size_t)V * attn_decode_tc_smem_per_warp()) + pair * 128;
+      if (b < B) {
+        if (p.dbg & 16) attention_decode_item_warp<bf16, ATT_CH>(a, b, head, pos, region, attbars + 2 * warp, lane, att_parity, part_i, 2, xch, pair + 1);  // A/B: the SIMT sweep
+        else attention_decode_item_warp_tc(a, b, head, pos, region, attbars + 2 * warp, lane, att_parity, part_i, 2, xch, pair + 1);
+      }
       prof_mark(prof, 5);
     }
     prof_mark(prof, 6);
@@ -535,8 +593,8 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     const int ntasks = p.K * p.V / 32;
     const float* c1 = reinterpret_cast<const float*>(blob + p.c_heads);
     const float* c2 = c1 + p.K * p.V;
-    if (tid == 64) {  // layer 0 of the NEXT token -> L2 (the cache outlives the kernel): its first phases start warm
-      for (int j = 0; j < JOBS_PER_LAYER; j++) prefetch_weight_job(j);
+    if (lane == 0) {  // layer 0 of the NEXT token -> L2 (the cache outlives the kernel): its first phases start warm
+      for (int j = 0; j < JOBS_PER_LAYER; j++) prefetch_weight_job_part(j, warp);
     }
     mbar_wait(abar, par_a, 3);
     par_a ^= 1u;
