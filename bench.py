@@ -69,13 +69,13 @@ def ncu_step_traffic():
         rows = list(csv.reader(open(p)))
         hdr = next(r for r in rows if "Kernel Name" in r)
         units = rows[rows.index(hdr) + 1]
-        data = next(r for r in rows[rows.index(hdr) + 2:] if len(r) == len(hdr) and "decode_step_kernel" in r[hdr.index("Kernel Name")])
+        data = next(r for r in rows[rows.index(hdr) + 2:] if len(r) == len(hdr) and "decode_step" in r[hdr.index("Kernel Name")])
         tot = 0.0
         for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = hdr.index(name)
             mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
             tot += float(data[i].replace(",", "")) * mult
-        return tot, "dram__bytes_read.sum + dram__bytes_write.sum of one decode_step_kernel launch, profiles/r02_step_raw.csv"
+        return tot, "dram__bytes_read.sum + dram__bytes_write.sum of one decode step kernel launch, profiles/r02_step_raw.csv"
     except Exception as ex:  # pragma: no cover
         return None, f"could not parse profiles/r02_step_raw.csv: {ex!r}"
 
@@ -489,14 +489,17 @@ def main():
                        "global_batch": world * B, "prompt_len": P_LEN, "desc_len": S_LEN, "parallelism": f"batch-shard x{world}",
                        "l2": f"inputs larger than L2 ({2 * step_weight_params(MODEL) / 1e9:.3f} GB weights + KV streamed per step)",
                        "timed_region": "generate_begin + prefill + sampling + fused decode steps",
-                       "decode_path": "fused persistent step kernel" if fused else "multi-kernel path (shape outside the fused kernel's range)"},
+                       "decode_path": {2: "cluster step kernel (step2.cu)", 1: "fused step kernel (step.cu)", 0: "multi-kernel path (shape outside the fused kernels' range)"}[int(fused)]},
             "clocks": clk,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_source": peak_src, "kernel": "decode_step_kernel (one persistent kernel per token: embed + L x layer phases + heads + sample)"
-                         if fused else "multi-kernel decode path", "ms_per_decode_step": dec_ms / n_timed, "algorithmic_bytes_per_step_avg": byts / n_timed},
+                         "peak_source": peak_src,
+                         "kernel": {2: "decode_step_cluster_kernel (one persistent kernel per token: 32 clusters x 4 CTAs, embed + L x 6 phases + heads + sample)",
+                                    1: "decode_step_kernel (one persistent kernel per token: 148 CTAs, embed + L x 8 phases + heads + sample)",
+                                    0: "multi-kernel decode path"}[int(fused)],
+                         "ms_per_decode_step": dec_ms / n_timed, "algorithmic_bytes_per_step_avg": byts / n_timed},
         }
         if dac_info is not None:
             line["dac_decode"] = dac_info

@@ -128,7 +128,8 @@ __device__ __forceinline__ unsigned grid_sync(unsigned* ctr, unsigned target, in
 // One warp's MMA loop: QN n-tiles x MT m-tiles over k-tiles [kt_lo, kt_hi) of the staged slice.  SETS independent accumulator
 // sets (k-tile parity x k16 half) break the dependent HMMA chain of the narrow phases (q = 1: out-proj, fc2 -- 32 dependent
 // MMAs at 16 k-tiles otherwise); they are summed in a fixed order at the end.  STATS: the warp also accumulates the LayerNorm
-// row sums of the k-tiles with (kt & 3) == dgrp from the A fragments it has loaded anyway.
+// row sums of its k-tiles from the A fragments it has loaded anyway (the four destination groups of a K half repeat this work:
+// 6 extra MMAs per k-tile and m-tile buy an exchange without any CTA-wide synchronisation).
 template <int QN, int MT, int SETS, bool STATS>
 __device__ __forceinline__ void mma_slice(float (&out)[2][6][4], RowStatFrag& rst, const bf16* xs, int apitch, const uint4* wb, int KT, int kt_lo,
                                           int kt_hi, int dgrp, int lrow, int lcol) {
@@ -151,7 +152,7 @@ __device__ __forceinline__ void mma_slice(float (&out)[2][6][4], RowStatFrag& rs
       for (int mt = 0; mt < MT; mt++)
 #pragma unroll
         for (int j = 0; j < 2; j++) ldsm4(a[mt][j], xs + (size_t)(mt * 16 + lrow) * apitch + kt * 32 + j * 16 + lcol);
-      if (STATS && (kt & 3) == dgrp) {
+      if (STATS) {   // every k-tile of this warp's K half: the (dest, K half) block then carries complete statistics for its K range
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) { row_stat_mma(rst, mt, a[mt][0]); row_stat_mma(rst, mt, a[mt][1]); }
       }
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   uint32_t par_a = 0, par_w = 0, par_x = 0, att_parity = 0;
 
   if (tid == 0) {
-    mbar_init(abar, 1); mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1); mbar_init(xbar, V * C);   // xbar: one arrival per warp of the cluster
+    mbar_init(abar, 1); mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1); mbar_init(xbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   attention_decode_init_warp(attbars + 2 * warp, lane);
@@ -365,7 +366,8 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     const int act_bytes = (rowpart ? 16 : ROWS) * apitch * 2;
     // exchange geometry: block (destination rank d, K half) at index 2 d + kh
     const int RS = (q == 1) ? 8 : 8 * q + 2;                         // floats per row of a feature-partitioned block
-    const int blk = rowpart ? 4 * Nc * 4 : ROWS * RS * 4;            // one (source rank, K half) accumulator slot of this CTA
+    const int blk = rowpart ? 32 + 4 * 8 * q * 4 : 256 + ROWS * RS * 4;   // one exchanged block: [statistics][rows][columns]
+    const int wsend = rowpart ? C * blk : blk;                       // bytes a warp stages (one block per destination rank)
     const int j0 = JOBS_PER_LAYER * l + (sub == 0 ? 0 : sub + 1);    // first weight job of this phase
     const int njobs = sub == 0 ? 2 : 1;
 
@@ -420,74 +422,76 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       if (sub == PH_O && l + 1 < p.L) prefetch_kv_part(l + 1, false, warp);
       if (sub == PH_OC && l + 1 < p.L) prefetch_kv_part(l + 1, true, warp);
     }
-    cluster_wait();  // every peer is past its previous epilogue: its receive slots are free
+    cluster_wait();  // every peer is past its previous epilogue: my send blocks have been read, its receive slots are free
 
-    // ---- partial sums straight into the destination ranks' receive slots (DSMEM stores from registers) ----
-    // accumulator slot v = 2 src_rank + K half; statistics slot = 8 src_rank + warp
-    const uint32_t recv_acc = s32(Rg) + (uint32_t)((act_bytes + 127) & ~127);
-    const uint32_t recv_st = recv_acc + (uint32_t)((V * blk + 127) & ~127);
-    const int stb = rowpart ? 32 : 256;   // bytes of one statistics slot: (S1, S2) of 4 / 32 rows
+    // ---- exchange: each warp stages its partial block in shared memory and ships it with ONE cp.async.bulk per destination
+    // (shared::cta -> shared::cluster, complete_tx on the destination's mbarrier); no CTA-wide synchronisation on the way ----
+    //   feature-partitioned: warp (dgrp, kh) -> rank dgrp, slot 2 rank + kh: [stats 32 x 2][32 rows][RS]
+    //   row-partitioned    : warp w -> every rank d, slot 8 rank + w:        [stats 4 x 2][4 rows][8 q]  (rows 4d..4d+3, the warp's columns)
+    const int nslots = rowpart ? V * C : V;
+    unsigned char* send = Rg + ((act_bytes + 127) & ~127);
+    unsigned char* recv = send + ((V * wsend + 127) & ~127);
+    if (tid == 0) mbar_expect_tx(xbar, (uint32_t)(nslots * blk));
     {
-      const uint32_t my_slot = recv_acc + (uint32_t)((2 * rank + kh) * blk);
-      if (!rowpart) {   // block [32 rows][RS]: everything rank dgrp finalises, this warp's K half
-        const uint32_t dst = mapa(my_slot, (uint32_t)dgrp);
+      unsigned char* mine = send + (size_t)warp * wsend;
+      if (!rowpart) {
+        float* bp = reinterpret_cast<float*>(mine + 256);
 #pragma unroll
         for (int mt = 0; mt < 2; mt++)
 #pragma unroll
           for (int j = 0; j < QMAX; j++) {
             if (j < q) {
-              const uint32_t o = dst + (uint32_t)(((mt * 16 + g) * RS + j * 8 + 2 * t4) * 4);
-              st_cluster_f2(o, acc[mt][j][0], acc[mt][j][1]);
-              st_cluster_f2(o + (uint32_t)(8 * RS * 4), acc[mt][j][2], acc[mt][j][3]);
+              float* base = bp + (size_t)(mt * 16 + g) * RS + j * 8 + 2 * t4;
+              *reinterpret_cast<float2*>(base) = make_float2(acc[mt][j][0], acc[mt][j][1]);
+              *reinterpret_cast<float2*>(base + 8 * RS) = make_float2(acc[mt][j][2], acc[mt][j][3]);
             }
           }
-      } else {          // block [4 rows][Nc] per destination: rows 4d..4d+3 of this cluster's half, all of the head's features
+        if (has_ln) {   // (S1, S2) of rows g / g+8 of each m-tile over this warp's K half (lane layout: ln_stats.cuh)
+          float* st = reinterpret_cast<float*>(mine);
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++) {
+            const int r0 = mt * 16 + g;
+            if (t4 == 0) { st[2 * r0] = rst.s1[mt][0]; st[2 * (r0 + 8)] = rst.s1[mt][2]; }
+            if (t4 == (g >> 1)) {
+              st[2 * r0 + 1] = (g & 1) ? rst.sq[mt][0][1] : rst.sq[mt][0][0];
+              st[2 * (r0 + 8) + 1] = (g & 1) ? rst.sq[mt][1][3] : rst.sq[mt][1][2];
+            }
+          }
+        }
+      } else {
+        const int qc = 8 * q;   // this warp's columns
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
           const int row = g + 8 * hh;
-          const uint32_t dst = mapa(my_slot, (uint32_t)(row >> 2)) + (uint32_t)(((row & 3) * Nc + dgrp * q * 8 + 2 * t4) * 4);
+          float* bp = reinterpret_cast<float*>(mine + (size_t)(row >> 2) * blk + 32) + (row & 3) * qc + 2 * t4;
 #pragma unroll
           for (int j = 0; j < QMAX; j++)
-            if (j < q) st_cluster_f2(dst + (uint32_t)(j * 32), acc[0][j][2 * hh], acc[0][j][2 * hh + 1]);
-        }
-      }
-      if (has_ln) {   // this warp's LayerNorm partial sums (one k-tile) of rows g / g+8 of each m-tile (lane layout: ln_stats.cuh)
-        const uint32_t my_st = recv_st + (uint32_t)((8 * rank + warp) * stb);
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++) {
-          if (mt < MT) {
-            const float s1a = rst.s1[mt][0], s1b = rst.s1[mt][2];
-            const float s2a = (g & 1) ? rst.sq[mt][0][1] : rst.sq[mt][0][0], s2b = (g & 1) ? rst.sq[mt][1][3] : rst.sq[mt][1][2];
-            const int r0 = mt * 16 + g, r1 = r0 + 8;
-            if (!rowpart) {
-#pragma unroll
-              for (int d = 0; d < C; d++) {
-                const uint32_t base = mapa(my_st, (uint32_t)d);
-                if (t4 == 0) { st_cluster_f1(base + r0 * 8, s1a); st_cluster_f1(base + r1 * 8, s1b); }
-                if (t4 == (g >> 1)) { st_cluster_f1(base + r0 * 8 + 4, s2a); st_cluster_f1(base + r1 * 8 + 4, s2b); }
-              }
-            } else {
-              const uint32_t b0 = mapa(my_st, (uint32_t)(r0 >> 2)) + (uint32_t)((r0 & 3) * 8), b1 = mapa(my_st, (uint32_t)(r1 >> 2)) + (uint32_t)((r1 & 3) * 8);
-              if (t4 == 0) { st_cluster_f1(b0, s1a); st_cluster_f1(b1, s1b); }
-              if (t4 == (g >> 1)) { st_cluster_f1(b0 + 4, s2a); st_cluster_f1(b1 + 4, s2b); }
-            }
-          }
+            if (j < q) *reinterpret_cast<float2*>(bp + j * 8) = make_float2(acc[0][j][2 * hh], acc[0][j][2 * hh + 1]);
+          float* st = reinterpret_cast<float*>(mine + (size_t)(row >> 2) * blk) + (row & 3) * 2;
+          if (t4 == 0) st[0] = hh ? rst.s1[0][2] : rst.s1[0][0];
+          if (t4 == (g >> 1)) st[1] = hh ? ((g & 1) ? rst.sq[0][1][3] : rst.sq[0][1][2]) : ((g & 1) ? rst.sq[0][0][1] : rst.sq[0][0][0]);
         }
       }
       __syncwarp();
-      if (lane < C) mbar_arrive_cluster(mapa(s32(xbar), (uint32_t)lane));   // one arrival per (warp, destination): 32 per CTA per phase
+      if (!rowpart) {
+        if (lane == 0) {
+          fence_proxy_async_smem();
+          bulk_s2peer(mapa(s32(recv + (size_t)(2 * rank + kh) * blk), (uint32_t)dgrp), mine, (uint32_t)blk, mapa(s32(xbar), (uint32_t)dgrp));
+        }
+      } else if (lane < C) {
+        fence_proxy_async_smem();
+        bulk_s2peer(mapa(s32(recv + (size_t)(8 * rank + warp) * blk), (uint32_t)lane), mine + (size_t)lane * blk, (uint32_t)blk, mapa(s32(xbar), (uint32_t)lane));
+      }
     }
     mbar_wait(xbar, par_x, 2);
     par_x ^= 1u;
     prof_mark(prof, 3);
 
-    // ---- epilogue: sum the 8 partial blocks in virtual-rank order, LayerNorm fix-up, activation / residual ----
-    const unsigned char* racc = Rg + ((act_bytes + 127) & ~127);
-    const unsigned char* rst_s = racc + ((V * blk + 127) & ~127);
+    // ---- epilogue: sum the partial blocks in a fixed order, LayerNorm fix-up, activation / residual ----
     if (!rowpart) {
       if (has_ln && tid < ROWS) {
         float S1 = 0.f, S2 = 0.f;
-        for (int v = 0; v < V * C; v++) { const float2 x = *reinterpret_cast<const float2*>(rst_s + (size_t)v * stb + tid * 8); S1 += x.x; S2 += x.y; }
+        for (int v = 0; v < V; v++) { const float2 x = *reinterpret_cast<const float2*>(recv + (size_t)v * blk + tid * 8); S1 += x.x; S2 += x.y; }
         const float mean = S1 / (float)H;
         stats[2 * tid] = mean;
         stats[2 * tid + 1] = rsqrtf(fmaxf(S2 / (float)H - mean * mean, 0.f) + p.eps);
@@ -499,7 +503,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
           const int f = f0 + 8 * i;
           float v = 0.f;
 #pragma unroll
-          for (int sv = 0; sv < V; sv++) v += reinterpret_cast<const float*>(racc + (size_t)sv * blk)[row * RS + f];
+          for (int sv = 0; sv < V; sv++) v += reinterpret_cast<const float*>(recv + (size_t)sv * blk + 256)[row * RS + f];
           if (sub == PH_FC1) {
             v = stats[2 * row + 1] * (v - stats[2 * row] * cvec[f]) + cvec[256 + f];
             v = apply_act(DT<bf16>::rnd(v), p.act);
@@ -513,9 +517,14 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         }
       }
     } else {
-      if (tid < 4) {  // rows 16 half + 4 rank + tid
+      const int qc = 8 * q;
+      if (tid < 4) {  // rows 16 half + 4 rank + tid: statistics from the dgrp == 0 warp of every (source rank, K half)
         float S1 = 0.f, S2 = 0.f;
-        for (int v = 0; v < V * C; v++) { const float2 x = *reinterpret_cast<const float2*>(rst_s + (size_t)v * stb + tid * 8); S1 += x.x; S2 += x.y; }
+        for (int sr = 0; sr < C; sr++)
+          for (int k2 = 0; k2 < 2; k2++) {
+            const float2 x = *reinterpret_cast<const float2*>(recv + (size_t)(8 * sr + 4 * k2) * blk + tid * 8);
+            S1 += x.x; S2 += x.y;
+          }
         const float mean = S1 / (float)H;
         stats[2 * tid] = mean;
         stats[2 * tid + 1] = rsqrtf(fmaxf(S2 / (float)H - mean * mean, 0.f) + p.eps);
@@ -524,16 +533,23 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       bf16* qkv_s = reinterpret_cast<bf16*>(Rg + QKV_OFF);  // [4][Nc]
       for (int idx = tid; idx < 4 * Nc; idx += THREADS) {
         const int r4 = idx / Nc, col = idx - r4 * Nc;
+        const int dg = col / qc, cw = col - dg * qc;           // the warps with dgrp == dg hold this column
         float v = 0.f;
 #pragma unroll
-        for (int sv = 0; sv < V; sv++) v += reinterpret_cast<const float*>(racc + (size_t)sv * blk)[r4 * Nc + col];
+        for (int sv = 0; sv < V; sv++)   // (source rank, K half) in order: warp index = 4 (sv & 1) + dg of rank sv >> 1
+          v += reinterpret_cast<const float*>(recv + (size_t)(8 * (sv >> 1) + 4 * (sv & 1) + dg) * blk + 32)[r4 * qc + cw];
         v = stats[2 * r4 + 1] * (v - stats[2 * r4] * cvec[col]) + cvec[256 + col];
         qkv_s[idx] = __float2bfloat16_rn(v);
       }
     }
     prof_mark(prof, 4);
-    __syncthreads();   // this CTA's receive slots are consumed (and q|k|v complete): peers may write the next phase's partials
+    __syncthreads();   // this CTA's receive slots are consumed (and q|k|v complete): peers may send the next phase's partials
     cluster_arrive();
+    if (rowpart) {
+      // attention scratch aliases the send blocks: the peers must have RECEIVED them (each is past its exchange wait) first
+      cluster_wait();
+      cluster_arrive();  // re-arm for the next phase's "exchange buffers free" wait
+    }
 
     // ---- attention of this rank's 4 (row, head) items: two warps per item ----
     if (rowpart) {
