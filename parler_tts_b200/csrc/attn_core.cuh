@@ -471,16 +471,46 @@ __device__ __forceinline__ uint32_t att_pack(float lo, float hi) {
 }
 
 constexpr int ATT_TC_CH = 16;   // keys per ring stage
-__host__ __device__ constexpr int attn_decode_tc_smem_per_warp() { return 2 * 2 * ATT_TC_CH * HD * 2 + (3 * HD) * (int)sizeof(float); }
+constexpr int ATT_TC_RING_BYTES = 2 * 2 * ATT_TC_CH * HD * 2;   // one warp's K/V ring: 8 KB
 
-// sm_warp must be 1024-byte aligned relative to nothing in particular (ldmatrix needs 16 B); bars: this warp's two mbarriers.
-__device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p, int b, int h, int pos, unsigned char* sm_warp, uint64_t* bars,
-                                                              int lane, uint32_t& parity, int part, int nparts, float* xch, int pair_bar) {
+// Requests the first two K/V stages of an item into the warp's ring (2 x 2 x 16 keys x 128 B at `ring`).  The cached rows do not
+// depend on the projection the same phase computes, so the cluster step kernel calls this right after its MMA loop -- a
+// microsecond or two before the attention itself starts -- and passes pre_issued = true below.
+__device__ __forceinline__ void attention_tc_issue_first(const AttnArgs& p, int b, int h, int pos, unsigned char* ring, uint64_t* bars, int lane,
+                                                         int part, int nparts) {
+  constexpr int CH = ATT_TC_CH;
+  const int n_cached = p.cross ? p.kv_len : pos;
+  const int n_chunks_all = (n_cached + CH - 1) / CH;
+  const int n_chunks = (n_chunks_all > part) ? (n_chunks_all - part + nparts - 1) / nparts : 0;
+  const bf16* kc = reinterpret_cast<const bf16*>(p.kcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
+  const bf16* vc = reinterpret_cast<const bf16*>(p.vcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
+  __syncwarp();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  for (int i = 0; i < 2 && i < n_chunks; i++) {
+    const int t0 = (part + nparts * i) * CH;
+    const int n = (n_cached - t0 < CH) ? (n_cached - t0) : CH;
+    const uint32_t bar = att_smem_u32(&bars[i]);
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * n * HD * 2)) : "memory");
+    __syncwarp();
+    if (lane < 2) {
+      const bf16* src = (lane == 0 ? kc : vc) + (size_t)t0 * HD;
+      bf16* dst = reinterpret_cast<bf16*>(ring) + (lane == 0 ? 0 : 2 * CH * HD) + i * CH * HD;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(att_smem_u32(dst)), "l"(src), "r"((uint32_t)(n * HD * 2)), "r"(bar) : "memory");
+    }
+  }
+}
+
+// ring: this warp's K/V stages ([2][16][64] K | [2][16][64] V, 16-byte aligned); fbuf: 192 floats (query, this step's key / value);
+// bars: this warp's two mbarriers.
+__device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p, int b, int h, int pos, unsigned char* ring, float* fbuf, uint64_t* bars,
+                                                              int lane, uint32_t& parity, int part, int nparts, float* xch, int pair_bar,
+                                                              long long* prof = nullptr, bool pre_issued = false) {
   constexpr int CH = ATT_TC_CH;
   constexpr int STAGE_ELEMS = CH * HD;
-  bf16* kst = reinterpret_cast<bf16*>(sm_warp);                 // [2][CH][64] swizzled rows
+  bf16* kst = reinterpret_cast<bf16*>(ring);                     // [2][CH][64] swizzled rows
   bf16* vst = kst + 2 * STAGE_ELEMS;
-  float* qs = reinterpret_cast<float*>(vst + 2 * STAGE_ELEMS);   // [64] query (fp32 of the bf16 values)
+  float* qs = fbuf;                                              // [64] query (fp32 of the bf16 values)
   float* kn = qs + HD;                                           // [64] this step's key   (self only)
   float* vn = kn + HD;                                           // [64] this step's value (self only)
   const bf16* __restrict__ rope_cos = reinterpret_cast<const bf16*>(p.rope_cos) + (size_t)pos * HD;
@@ -517,10 +547,12 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     parity ^= (1u << st);
   };
 
-  __syncwarp();
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  if (n_chunks > 0) issue(0);
-  if (n_chunks > 1) issue(1);
+  if (!pre_issued) {
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (n_chunks > 0) issue(0);
+    if (n_chunks > 1) issue(1);
+  }
 
   // query (+ rotary), this step's K/V row (self): to the cache and to shared memory
   {
@@ -558,6 +590,7 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     qa2[ks] = (g == 0) ? att_pack(qs[16 * ks + 8 + 2 * t], qs[16 * ks + 8 + 2 * t + 1]) : 0u;
   }
   const int* km = p.key_mask ? p.key_mask + (size_t)b * p.mask_ld : nullptr;
+  if (prof != nullptr && lane == 0) prof[8] = clock64();   // set-up done (query, K/V append, first two stages requested)
   float m_run = -INFINITY, l_run = 0.f;
   float o[8][4];
 #pragma unroll
@@ -638,6 +671,7 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
       issue(c + 2);
     }
   }
+  if (prof != nullptr && lane == 0) { prof[9] = clock64(); prof[11] = n_chunks; }   // cached keys swept
   // lanes 0..3 hold the output row: o[j][0], o[j][1] = dims 8 j + 2 t, 8 j + 2 t + 1
   if (!p.cross && part == 0) {  // the step's own key (position `pos`), from shared memory
     float sdot = 0.f;
@@ -684,6 +718,7 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     }
     asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
   }
+  if (prof != nullptr && lane == 0) prof[10] = clock64();    // merged with the partner warp
   if (lane < 4 && part == 0) {
     const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;  // fully masked row -> zeros (never consumed)
     bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)b * p.ldo + h * HD;

@@ -39,6 +39,7 @@ constexpr int V = 8;            // virtual ranks = warps per CTA: warp w reduces
 constexpr int THREADS = 256;
 constexpr int ROWS = 32;        // batch rows (two m16 tiles; the head phases work on one half = one m16 tile)
 constexpr int ATT_CH = 16;      // keys per K/V ring stage of an attention warp
+constexpr int PROF_STRIDE = 16;  // clock64 stamps per phase row of the optional profile buffer (tools/profile_step2.py)
 constexpr int QMAX = 6;         // n-tiles per warp (QKV: 24 n-tiles of a head over 4 destination groups)
 constexpr int OFF_STATS = 256, OFF_PART = 512, OFF_RES = 2560, OFF_CVEC = 3584;
 constexpr int HDR = 5632;       // mbarriers | row stats | stat partials | residual slice | folded-LN vectors c1[256] c2[256]
@@ -106,7 +107,7 @@ __device__ __forceinline__ void prof_mark(long long* prof, int slot) { if (prof 
 // `post` runs on thread 0 the moment the barrier opens (before the CTA is released): the next phase's activation copy.
 // `side` runs on thread 32 while thread 0 polls.
 template <typename Post, typename Side>
-__device__ __forceinline__ unsigned grid_sync(unsigned* ctr, unsigned target, int ph, Post post, Side side) {
+__device__ __forceinline__ unsigned grid_sync(unsigned* ctr, unsigned target, int ph, Post post, Side side, bool acq_fence = true) {
   target += gridDim.x;
   asm volatile("fence.proxy.async.global;" ::: "memory");  // this thread's global writes -> other CTAs' TMA reads (writer side)
   __syncthreads();
@@ -116,7 +117,10 @@ __device__ __forceinline__ unsigned grid_sync(unsigned* ctr, unsigned target, in
     while (ld_relaxed(ctr) < target) {
       if (++spins > (1u << 24)) { printf("ptts: cluster step grid barrier timeout (cta %d target %u seen %u phase %d)\n", (int)blockIdx.x, target, ld_relaxed(ctr), ph); __trap(); }
     }
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    // Everything this kernel reads that another CTA wrote during the same launch goes through L2 (TMA bulk copies of the images
+    // and the K/V rows, __ldcg of the logits / EOS columns), so the L1 invalidation of an acquire fence protects nothing here and
+    // costs 0.4 us per barrier (profiles/r02_step2_phases.md): the per-layer barriers skip it, PTTS_DBG=32 puts it back.
+    if (acq_fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
     post();
   } else if (threadIdx.x == 32) {
     side();
@@ -211,7 +215,7 @@ template <int ITEMS>
 __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   Ctrl* ctrl = p.sa.ctrl;
-  if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(size_t)(6 * p.L + 2) * 8 + 3] = clock64();
+  if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(size_t)(6 * p.L + 2) * PROF_STRIDE + 3] = clock64();
   if (ctrl->active == 0) return;  // generation finished: the rest of the enqueued steps are no-ops (uniform over the grid)
   const int cur_len = ctrl->cur_len;
   const unsigned gen = (unsigned)ctrl->launch_gen;
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   attention_decode_init_warp(attbars + 2 * warp, lane);
   cluster_arrive(); cluster_wait();   // every peer's mbarriers exist before any remote complete_tx
   cluster_arrive();                   // pre-arm: pairs with the first phase's "exchange buffers free" wait
+  const bool acq = (p.dbg & 32) != 0;   // PTTS_DBG=32: put the acquire fence back (grid_sync explains why it is not needed)
   unsigned* const bar_ctr = p.bar + (gen & 1u);
   unsigned bar_target = 0u;
   if (cta == 0 && tid == 0) p.bar[(gen + 1u) & 1u] = 0u;  // the counter the NEXT launch will use
@@ -342,7 +347,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   {
     const bf16* nimg; uint32_t nbytes;
     slice_of(PH_QKV, nimg, nbytes);
-    bar_target = grid_sync(bar_ctr, bar_target, -1, [&]() { request_slice(nimg, nbytes); }, []() {});
+    bar_target = grid_sync(bar_ctr, bar_target, -1, [&]() { request_slice(nimg, nbytes); }, []() {}, acq);
   }
   prof_mark(prof, 7);
 
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
 #pragma unroll 1
   for (int ph = 0; ph < n_phases; ph++) {
     const int l = ph / 6, sub = ph - 6 * l;
-    prof = prof0 ? prof0 + (size_t)(ph + 1) * 8 : nullptr;
+    prof = prof0 ? prof0 + (size_t)(ph + 1) * PROF_STRIDE : nullptr;
     prof_mark(prof, 0);
     const char* lb = blob + p.layer0 + p.layer_stride * l;
     const bool rowpart = (sub == PH_QKV || sub == PH_QC);
@@ -371,7 +376,9 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     const int j0 = JOBS_PER_LAYER * l + (sub == 0 ? 0 : sub + 1);    // first weight job of this phase
     const int njobs = sub == 0 ? 2 : 1;
 
-    // folded-LayerNorm vectors of this phase's features (read after two CTA barriers)
+    // folded-LayerNorm vectors of this phase's features: requested now, parked in shared memory after the MMA loop (a global
+    // load followed at once by its shared-memory store would park the warp for an L2 round trip in front of the MMAs)
+    float cv1 = 0.f, cv2 = 0.f;
     if (has_ln) {
       const float* c1; int ntot;
       if (sub == PH_QKV) { c1 = reinterpret_cast<const float*>(lb + p.c_qkv); ntot = p.qkv_rows; }
@@ -383,8 +390,8 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         if (sub == PH_QKV) n = (tid >> 6) * (p.nh * HD) + head * HD + (tid & 63);
         else if (sub == PH_QC) n = head * HD + tid;
         else n = cta * 8 * q + tid;
-        cvec[tid] = c1[n];
-        cvec[256 + tid] = c1[ntot + n];
+        cv1 = c1[n];
+        cv2 = c1[ntot + n];
       }
     }
 
@@ -415,12 +422,64 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       } else mma_slice<1, 2, 4, false>(acc, rst, xs, apitch, wb, KT, kt_lo, kt_hi, dgrp, lrow, lcol);
     }
     prof_mark(prof, 2);
+    if (has_ln && tid < (rowpart ? Nc : 8 * q)) { cvec[tid] = cv1; cvec[256 + tid] = cv2; }   // read in the epilogue, several barriers later
     __syncthreads();  // activation slice and weight buffer(s) are dead
     if (lane == 0) {  // asynchronous requests, one or two per warp so that no single thread holds the CTA back
-      if (warp == 1) for (int i = 0; i < njobs; i++) issue_weight_job(j0 + i + 2);   // refill the ring two jobs ahead
+      if (warp == 1 && sub != PH_QC) for (int i = 0; i < njobs; i++) issue_weight_job(j0 + i + 2);   // refill the ring two jobs ahead
+      // (q_cross holds fc1's weights back until its attention is done: the K/V rings live in that buffer meanwhile)
       for (int i = 0; i < njobs; i++) prefetch_weight_job_part(j0 + i + JOBS_PER_LAYER, warp);  // same job, next layer (or lm heads) -> L2
+      if (sub == PH_QKV && warp == 2 && l + 1 < p.L) {   // next layer's folded-LN vectors: every CTA pulls a 1/grid share into L2
+        const int64_t c_bytes = p.c_fc1 + (int64_t)2 * F * 4 - p.c_qkv;
+        const uint32_t share = (uint32_t)(((c_bytes / (int)gridDim.x) + 15) & ~15);
+        const int64_t o = (int64_t)cta * share;
+        if (o < c_bytes) l2_prefetch(lb + p.layer_stride + p.c_qkv + o, (uint32_t)(c_bytes - o < share ? c_bytes - o : share));
+      }
       if (sub == PH_O && l + 1 < p.L) prefetch_kv_part(l + 1, false, warp);
       if (sub == PH_OC && l + 1 < p.L) prefetch_kv_part(l + 1, true, warp);
+    }
+    // The attention of the head phases: build its arguments and request the first two K/V stages of this warp's item now.
+    // The rings live in the weight ring's idle space (the phase's own weights are dead, the next jobs fill only the heads of the
+    // buffers), so they alias nothing the exchange uses and can fill while it runs.
+    AttnArgs att{};
+    int att_b = B;
+    unsigned char* att_ring = nullptr; float* att_f = nullptr; float* att_xch = nullptr;
+    if (rowpart) {
+      att.ctrl = nullptr; att.B = B; att.nh = p.nh; att.nkv = p.nh; att.q_len = 1;
+      att.past_from_ctrl = 0; att.past_len = pos; att.prefix = p.P;
+      att.rope = p.rope; att.rope_cos = blob + p.rope_cos; att.rope_sin = blob + p.rope_sin; att.scale = p.scale;
+      const bf16* qkv_s = reinterpret_cast<const bf16*>(Rg + QKV_OFF);
+      const int row_base = 16 * half + 4 * rank;
+      // row b = row_base + i, head: q at qkv_s[i][0..63] (k at +64, v at +128 for the self phase)
+      const bf16* qbase = qkv_s - (size_t)row_base * Nc - (size_t)head * HD;
+      att.q = qbase; att.ldq = Nc; att.q_col0 = 0;
+      att.ldo = pitch;   // attn image: row b, head h -> slice h / 4, column (h % 4) * 64
+      att.out = a_img + (size_t)(head >> 2) * x_slice_elems + (head & 3) * HD - (size_t)head * HD;
+      unsigned char* wb0 = smem + HDR;   // the two weight ring buffers
+      if (sub == PH_QKV) {
+        att.knew = qbase; att.vnew = qbase; att.ldkv = Nc; att.k_col0 = HD; att.v_col0 = 2 * HD;
+        char* kc = p.self_kv + p.self_layer_stride * l;
+        att.kcache = kc; att.vcache = kc + (size_t)B * p.nh * p.Tmax * HD * 2;
+        att.kv_b_stride = (int64_t)p.nh * p.Tmax * HD; att.kv_h_stride = (int64_t)p.Tmax * HD; att.kv_t_stride = HD;
+        att.key_mask = p.prompt_mask; att.mask_len = p.P; att.mask_ld = p.P;
+        att.cross = 0; att.kv_len = 0; att.kv_capacity = p.Tmax;
+        // out-proj's 16 KB go to the head of buffer (j0+2)&1, q_cross's 32 KB to the head of the other one
+        unsigned char* bB = wb0 + ((j0 + 2) & 1) * WB_BYTES; unsigned char* bC = wb0 + ((j0 + 3) & 1) * WB_BYTES;
+        att_ring = warp < 6 ? bB + 16384 + warp * ATT_TC_RING_BYTES : bC + 32768 + (warp - 6) * ATT_TC_RING_BYTES;
+        att_xch = reinterpret_cast<float*>(bC + 49152) + (warp >> 1) * 128;
+      } else {
+        att.knew = nullptr; att.vnew = nullptr;
+        char* ck = p.cross_kv + p.cross_layer_stride * l;
+        att.kcache = ck; att.vcache = ck + (size_t)B * p.nh * p.S * HD * 2;
+        att.kv_b_stride = (int64_t)p.nh * p.S * HD; att.kv_h_stride = (int64_t)p.S * HD; att.kv_t_stride = HD;
+        att.key_mask = p.enc_mask; att.mask_len = p.S; att.mask_ld = p.S;
+        att.cross = 1; att.kv_len = p.S; att.kv_capacity = p.S;
+        // this phase's own (dead) weight buffer holds the rings; cross out-proj's 16 KB sit at the head of the other one
+        att_ring = wb0 + (j0 & 1) * WB_BYTES + warp * ATT_TC_RING_BYTES;
+        att_xch = reinterpret_cast<float*>(wb0 + ((j0 + 1) & 1) * WB_BYTES + 16384) + (warp >> 1) * 128;
+      }
+      att_f = reinterpret_cast<float*>(Rg + 65536) + warp * 192;   // query / new key / new value: a corner of R the exchange never uses
+      att_b = row_base + (warp >> 1);
+      if (att_b < B && !(p.dbg & 16)) attention_tc_issue_first(att, att_b, head, pos, att_ring, attbars + 2 * warp, lane, warp & 1, 2);
     }
     cluster_wait();  // every peer is past its previous epilogue: my send blocks have been read, its receive slots are free
 
@@ -545,50 +604,29 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     prof_mark(prof, 4);
     __syncthreads();   // this CTA's receive slots are consumed (and q|k|v complete): peers may send the next phase's partials
     cluster_arrive();
-    if (rowpart) {
-      // attention scratch aliases the send blocks: the peers must have RECEIVED them (each is past its exchange wait) first
+    if (rowpart && (p.dbg & 16)) {
+      // the SIMT attention's scratch aliases the send blocks: the peers must have RECEIVED them (each is past its exchange wait) first
       cluster_wait();
       cluster_arrive();  // re-arm for the next phase's "exchange buffers free" wait
     }
 
-    // ---- attention of this rank's 4 (row, head) items: two warps per item ----
+    // ---- attention of this rank's 4 (row, head) items: two warps per item (first two K/V stages were requested after the MMA) ----
     if (rowpart) {
-      AttnArgs a{};
-      a.ctrl = nullptr; a.B = B; a.nh = p.nh; a.nkv = p.nh; a.q_len = 1;
-      a.past_from_ctrl = 0; a.past_len = pos; a.prefix = p.P;
-      a.rope = p.rope; a.rope_cos = blob + p.rope_cos; a.rope_sin = blob + p.rope_sin; a.scale = p.scale;
-      const bf16* qkv_s = reinterpret_cast<const bf16*>(Rg + QKV_OFF);
-      const int row_base = 16 * half + 4 * rank;
-      // row b = row_base + i, head: q at qkv_s[i][0..63] (k at +64, v at +128 for the self phase)
-      const bf16* qbase = qkv_s - (size_t)row_base * Nc - (size_t)head * HD;
-      a.q = qbase; a.ldq = Nc; a.q_col0 = 0;
-      // attn image: row b, head h -> slice h / 4, column (h % 4) * 64
-      a.ldo = pitch;
-      a.out = a_img + (size_t)(head >> 2) * x_slice_elems + (head & 3) * HD - (size_t)head * HD;
-      if (sub == PH_QKV) {
-        a.knew = qbase; a.vnew = qbase; a.ldkv = Nc; a.k_col0 = HD; a.v_col0 = 2 * HD;
-        char* kc = p.self_kv + p.self_layer_stride * l;
-        a.kcache = kc; a.vcache = kc + (size_t)B * p.nh * p.Tmax * HD * 2;
-        a.kv_b_stride = (int64_t)p.nh * p.Tmax * HD; a.kv_h_stride = (int64_t)p.Tmax * HD; a.kv_t_stride = HD;
-        a.key_mask = p.prompt_mask; a.mask_len = p.P; a.mask_ld = p.P;
-        a.cross = 0; a.kv_len = 0; a.kv_capacity = p.Tmax;
-      } else {
-        a.knew = nullptr; a.vnew = nullptr;
-        char* ck = p.cross_kv + p.cross_layer_stride * l;
-        a.kcache = ck; a.vcache = ck + (size_t)B * p.nh * p.S * HD * 2;
-        a.kv_b_stride = (int64_t)p.nh * p.S * HD; a.kv_h_stride = (int64_t)p.S * HD; a.kv_t_stride = HD;
-        a.key_mask = p.enc_mask; a.mask_len = p.S; a.mask_ld = p.S;
-        a.cross = 1; a.kv_len = p.S; a.kv_capacity = p.S;
-      }
-      const int pair = warp >> 1, part_i = warp & 1;
-      const int b = row_base + pair;
-      unsigned char* region = Rg + (size_t)warp * attn_decode_tc_smem_per_warp();
-      float* xch = reinterpret_cast<float*>(Rg + (size_t)V * attn_decode_tc_smem_per_warp()) + pair * 128;
-      if (b < B) {
-        if (p.dbg & 16) attention_decode_item_warp<bf16, ATT_CH>(a, b, head, pos, region, attbars + 2 * warp, lane, att_parity, part_i, 2, xch, pair + 1);  // A/B: the SIMT sweep
-        else attention_decode_item_warp_tc(a, b, head, pos, region, attbars + 2 * warp, lane, att_parity, part_i, 2, xch, pair + 1);
+      if (att_b < B) {
+        if (p.dbg & 16) {  // A/B: the SIMT sweep (its ring layout: K/V stages then 192 floats, inside the R region)
+          unsigned char* region = Rg + (size_t)warp * attn_decode_smem_per_warp<bf16, ATT_CH>();
+          float* xr = reinterpret_cast<float*>(Rg + (size_t)V * attn_decode_smem_per_warp<bf16, ATT_CH>()) + (warp >> 1) * 128;
+          attention_decode_item_warp<bf16, ATT_CH>(att, att_b, head, pos, region, attbars + 2 * warp, lane, att_parity, warp & 1, 2, xr, (warp >> 1) + 1);
+        } else {
+          attention_decode_item_warp_tc(att, att_b, head, pos, att_ring, att_f, attbars + 2 * warp, lane, att_parity, warp & 1, 2, att_xch, (warp >> 1) + 1,
+                                        warp == 0 ? prof : nullptr, true);
+        }
       }
       prof_mark(prof, 5);
+      if (sub == PH_QC) {   // fc1's weights were held back: the K/V rings used their buffer
+        __syncthreads();
+        if (tid == 32) issue_weight_job(j0 + 2);
+      }
     }
     prof_mark(prof, 6);
 
@@ -597,13 +635,13 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     const bf16* nimg; uint32_t nbytes;
     if (last) { nimg = x_img; nbytes = (uint32_t)(C * x_slice_elems * 2); }   // lm heads: the whole x image
     else slice_of((sub + 1) % 6, nimg, nbytes);
-    bar_target = grid_sync(bar_ctr, bar_target, ph, [&]() { request_slice(nimg, nbytes); }, []() {});
+    bar_target = grid_sync(bar_ctr, bar_target, ph, [&]() { request_slice(nimg, nbytes); }, []() {}, acq);
     prof_mark(prof, 7);
   }
   cluster_wait();  // balance the last phase's arrive
 
   // ---- final LayerNorm + K lm heads: N-split over all CTAs (4 n-tiles per task, full K), no exchange ----
-  prof = prof0 ? prof0 + (size_t)(n_phases + 1) * 8 : nullptr;
+  prof = prof0 ? prof0 + (size_t)(n_phases + 1) * PROF_STRIDE : nullptr;
   prof_mark(prof, 0);
   {
     const int ntasks = p.K * p.V / 32;
@@ -692,7 +730,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   }
   prof_mark(prof, 6);
   bar_target = grid_sync(bar_ctr, bar_target, n_phases, []() {}, []() {});
-  prof = prof0 ? prof0 + (size_t)(n_phases + 2) * 8 : nullptr;  // tail row: sampling / barrier
+  prof = prof0 ? prof0 + (size_t)(n_phases + 2) * PROF_STRIDE : nullptr;  // tail row: sampling / barrier
   prof_mark(prof, 0);
   if (p.do_sample_phase) {
     const ptts_gen_params gp = *p.sa.gen;

@@ -26,7 +26,8 @@ assert sess.fused == 2, f"cluster step kernel not in use (fused kind {sess.fused
 sess.sample()
 sess.decode_steps(steps_before)
 nph = 6 * NL
-buf = torch.zeros((8 * NL + 3) * 8, dtype=torch.int64, device=dev)
+STRIDE = 16
+buf = torch.zeros((6 * NL + 4) * STRIDE, dtype=torch.int64, device=dev)
 _lib.check(_lib.lib().ptts_session_set_profile(sess.h, _lib.ptr(buf)))
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -34,7 +35,7 @@ e0.record()
 sess.decode_steps(1)
 e1.record()
 torch.cuda.synchronize()
-t = buf.cpu().view(-1, 8).numpy()
+t = buf.cpu().view(-1, STRIDE).numpy()
 _lib.check(_lib.lib().ptts_session_set_profile(sess.h, None))
 us = lambda c: c / 1.965 / 1e3
 names = ["qkv+self-attn", "o-proj", "q_cross+cross-attn", "o_cross", "fc1", "fc2"]
@@ -51,8 +52,12 @@ for sub in range(6):
     work = us(rows[:, 6] - rows[:, 0])
     out[names[sub]] = dict(work=work.mean(), barrier=barr.mean(), wait=wait.mean(), mma=mma.mean(), exch=exch.mean(), epi=epi.mean(), attn=attn.mean())
     tot_l += work.mean() + barr.mean()
+    extra = ""
+    if sub in (0, 2):   # attention internals (warp 0): cluster sync + set-up | ring sweep | own key + merge | store
+        extra = (f"  [attn: setup {us(rows[:, 8] - rows[:, 4]).mean():.2f} sweep {us(rows[:, 9] - rows[:, 8]).mean():.2f} ({rows[:, 11].mean():.1f} chunks)"
+                 f" merge {us(rows[:, 10] - rows[:, 9]).mean():.2f} store {us(rows[:, 5] - rows[:, 10]).mean():.2f}]")
     print(f"{names[sub]:20s} work {work.mean():6.2f}  barrier {barr.mean():5.2f} | wait {wait.mean():5.2f}  mma {mma.mean():5.2f}  exch {exch.mean():5.2f}"
-          f"  epi {epi.mean():5.2f}  attn {attn.mean():5.2f}")
+          f"  epi {epi.mean():5.2f}  attn {attn.mean():5.2f}{extra}")
 print(f"per layer {tot_l:.1f} us -> {tot_l * NL:.0f} us for {NL} layers")
 r0, rh, rt = t[0], t[nph + 1], t[nph + 2]
 print(f"prologue {us(r0[0] - rt[3]):.2f} | embed {us(r0[6] - r0[0]):.2f} + barrier {us(r0[7] - r0[6]):.2f} | lm heads {us(rh[6] - rh[0]):.2f} "
