@@ -504,14 +504,59 @@ class ParlerTTSForConditionalGeneration:
         return self
 
     # -- side inputs (not replaced; PyTorch) -------------------------------------------------------
+    def _encode_text_eager(self, input_ids, attention_mask):
+        h = self.text_encoder(input_ids=input_ids, attention_mask=attention_mask, return_dict=True).last_hidden_state
+        if self.enc_to_dec_proj is not None:
+            h = torch.nn.functional.linear(h, *self.enc_to_dec_proj)        # :2388-2392 / :3087-3090
+        if attention_mask is not None:
+            h = h * attention_mask[..., None]                               # :3092-3093
+        return h.to(self.dtype)
+
     def _encode_text(self, input_ids, attention_mask):
+        """Description ids -> encoder_hidden_states (reference :3048-3097): T5 encoder + enc_to_dec_proj + mask multiply.
+        These PyTorch modules are not replaced; what this path adds is ONE CUDA graph per (batch, length) shape
+        over the whole chain -- a T5 encoder is ~150 small launches whose launch latency, not their math, is the time-to-first-audio
+        once the decode loop is fast.  Inputs are copied into static buffers and the graph is replayed; if capture is impossible
+        (a module that synchronises), the eager path is used and said so once."""
         if self.text_encoder is None:
             raise ValueError("this model was built without a text encoder: pass `encoder_outputs`")
-        with torch.no_grad():
-            h = self.text_encoder(input_ids=input_ids, attention_mask=attention_mask, return_dict=True).last_hidden_state
-        if self.enc_to_dec_proj is not None:
-            h = torch.nn.functional.linear(h, *self.enc_to_dec_proj)
-        return h
+        input_ids = input_ids.to(self.device)
+        attention_mask = None if attention_mask is None else attention_mask.to(self.device)
+        if not hasattr(self, "_enc_graphs"):
+            self._enc_graphs, self._enc_graph_ok = {}, os.environ.get("PTTS_ENCODER_GRAPH", "1") != "0"
+        if not self._enc_graph_ok or self.device.type != "cuda":
+            return self._encode_text_eager(input_ids, attention_mask)
+        key = (tuple(input_ids.shape), attention_mask is not None)
+        entry = self._enc_graphs.get(key)
+        if entry is None:
+            try:
+                s_ids = input_ids.clone()
+                s_mask = None if attention_mask is None else attention_mask.clone()
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    for _ in range(2):                                   # warm-up: lazy initialisations happen outside the capture
+                        self._encode_text_eager(s_ids, s_mask)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    s_out = self._encode_text_eager(s_ids, s_mask)
+                entry = (graph, s_ids, s_mask, s_out)
+                if len(self._enc_graphs) >= 16:
+                    self._enc_graphs.clear()
+                self._enc_graphs[key] = entry
+            except Exception as ex:  # pragma: no cover - depends on the encoder implementation
+                import warnings
+                warnings.warn(f"text-encoder CUDA graph capture failed ({ex!r}); running the encoder eagerly")
+                self._enc_graph_ok = False
+                torch.cuda.synchronize(self.device)
+                return self._encode_text_eager(input_ids, attention_mask)
+        graph, s_ids, s_mask, s_out = entry
+        s_ids.copy_(input_ids)
+        if s_mask is not None:
+            s_mask.copy_(attention_mask)
+        graph.replay()
+        return s_out.clone()
 
     # -- generate with user-supplied processors / stopping criteria --------------------------------
     def _host_driven_loop(self, sess: "GenSession", gc, max_length, user_processors, user_criteria, streamer, seed):
@@ -607,9 +652,7 @@ class ParlerTTSForConditionalGeneration:
         else:
             if input_ids is None:
                 raise ValueError("generate() needs `input_ids` (description) or `encoder_outputs`")
-            enc_hidden = self._encode_text(input_ids.to(self.device), None if attention_mask is None else attention_mask.to(self.device))
-            if attention_mask is not None:
-                enc_hidden = enc_hidden * attention_mask.to(self.device)[..., None]  # :3092-3093
+            enc_hidden = self._encode_text(input_ids, attention_mask)   # encoder + enc_to_dec_proj + mask multiply, one CUDA graph
         enc_hidden = enc_hidden.to(self.device, self.dtype)
         B, S, _ = enc_hidden.shape
         prompt_hidden = mk.get("prompt_hidden_states")
