@@ -87,7 +87,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes, bool on = true) {
+  if (!on) return;
   const char* c = reinterpret_cast<const char*>(p);
   while (bytes > 0) {
     const uint32_t n = bytes > 32768u ? 32768u : bytes;
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   attention_decode_init_warp(attbars + 2 * warp, lane);
   cluster_arrive(); cluster_wait();   // every peer's mbarriers exist before any remote complete_tx
   cluster_arrive();                   // pre-arm: pairs with the first phase's "exchange buffers free" wait
+  const bool pf_on = !(p.dbg & 1);      // PTTS_DBG=1: no L2 prefetches (measurement switch)
   const bool acq = (p.dbg & 32) != 0;   // PTTS_DBG=32: put the acquire fence back (grid_sync explains why it is not needed)
   unsigned* const bar_ctr = p.bar + (gen & 1u);
   unsigned bar_target = 0u;
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   };
   auto prefetch_weight_job = [&](int j) {  // ONE thread: HBM -> L2, a layer ahead
     const char* src; uint32_t bytes;
-    if (weight_job(p, j, cta, rank, src, bytes)) l2_prefetch(src, bytes);
+    if (pf_on && weight_job(p, j, cta, rank, src, bytes)) l2_prefetch(src, bytes);
   };
   // K/V rows of this rank's 4 attention items (rows 16 half + 4 rank .. + 3, head) -> L2
   auto prefetch_kv = [&](int l, bool cross) {  // ONE thread
@@ -288,12 +290,12 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   // the same requests cut into one piece per warp (issued by lane 0 of every warp: a prefetch is ~100 cycles of issue time)
   auto prefetch_weight_job_part = [&](int j, int w) {
     const char* src; uint32_t bytes;
-    if (weight_job(p, j, cta, rank, src, bytes)) { const uint32_t pc = (bytes / V) & ~15u; l2_prefetch(src + (size_t)w * pc, w == V - 1 ? bytes - (V - 1) * pc : pc); }
+    if (pf_on && weight_job(p, j, cta, rank, src, bytes)) { const uint32_t pc = (bytes / V) & ~15u; l2_prefetch(src + (size_t)w * pc, w == V - 1 ? bytes - (V - 1) * pc : pc); }
   };
   auto prefetch_kv_part = [&](int l, bool cross, int w) {  // warp w: item w >> 1, K (even w) or V (odd w)
     const int T = cross ? p.S : p.Tmax, n = cross ? p.S : pos;
     const int b = 16 * half + 4 * rank + (w >> 1);
-    if (n <= 0 || b >= B) return;
+    if (!pf_on || n <= 0 || b >= B) return;
     const char* kc = cross ? p.cross_kv + p.cross_layer_stride * l : p.self_kv + p.self_layer_stride * l;
     const char* k = kc + ((size_t)b * p.nh + head) * T * HD * 2 + ((w & 1) ? (size_t)B * p.nh * T * HD * 2 : 0);
     l2_prefetch(k, (uint32_t)(n * HD * 2));
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         const int64_t c_bytes = p.c_fc1 + (int64_t)2 * F * 4 - p.c_qkv;
         const uint32_t share = (uint32_t)(((c_bytes / (int)gridDim.x) + 15) & ~15);
         const int64_t o = (int64_t)cta * share;
-        if (o < c_bytes) l2_prefetch(lb + p.layer_stride + p.c_qkv + o, (uint32_t)(c_bytes - o < share ? c_bytes - o : share));
+        if (pf_on && o < c_bytes) l2_prefetch(lb + p.layer_stride + p.c_qkv + o, (uint32_t)(c_bytes - o < share ? c_bytes - o : share));
       }
       if (sub == PH_O && l + 1 < p.L) prefetch_kv_part(l + 1, false, warp);
       if (sub == PH_OC && l + 1 < p.L) prefetch_kv_part(l + 1, true, warp);
@@ -557,7 +559,23 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       }
       if (has_ln) __syncthreads();
       const int row = tid >> 3, f0 = tid & 7;
-      if (row < B) {
+      if (row < B && sub == PH_FC1 && q == 4) {   // 4 consecutive features per thread: 8-byte loads, one 8-byte store
+        const int f = 4 * f0;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int sv = 0; sv < V; sv++) {
+          const float* bp = reinterpret_cast<const float*>(recv + (size_t)sv * blk + 256) + row * RS + f;
+          const float2 a = *reinterpret_cast<const float2*>(bp), b2 = *reinterpret_cast<const float2*>(bp + 2);
+          v[0] += a.x; v[1] += a.y; v[2] += b2.x; v[3] += b2.y;
+        }
+        const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = apply_act(DT<bf16>::rnd(rstd * (v[e] - mean * cvec[f + e]) + cvec[256 + f + e]), p.act);
+        const int n = cta * 32 + f;
+        uint2 pk;
+        pk.x = att_pack(v[0], v[1]); pk.y = att_pack(v[2], v[3]);
+        *reinterpret_cast<uint2*>(h_img + (size_t)(n / KsF) * h_slice_elems + row * pitchF + (n % KsF)) = pk;
+      } else if (row < B) {
         for (int i = 0; i < q; i++) {
           const int f = f0 + 8 * i;
           float v = 0.f;

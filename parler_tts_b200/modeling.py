@@ -505,7 +505,13 @@ class ParlerTTSForConditionalGeneration:
 
     # -- side inputs (not replaced; PyTorch) -------------------------------------------------------
     def _encode_text_eager(self, input_ids, attention_mask):
-        h = self.text_encoder(input_ids=input_ids, attention_mask=attention_mask, return_dict=True).last_hidden_state
+        enc_mask = attention_mask
+        if attention_mask is not None and attention_mask.dim() == 2:
+            # the 4-D additive form HF derives from a 2-D padding mask (0 keep / finfo.min drop), built here with device ops only:
+            # the library's own conversion creates CPU scalars on the way, which a CUDA-graph capture cannot contain
+            edt = next(self.text_encoder.parameters()).dtype
+            enc_mask = (1 - attention_mask)[:, None, None, :].to(edt) * torch.finfo(edt).min
+        h = self.text_encoder(input_ids=input_ids, attention_mask=enc_mask, return_dict=True).last_hidden_state
         if self.enc_to_dec_proj is not None:
             h = torch.nn.functional.linear(h, *self.enc_to_dec_proj)        # :2388-2392 / :3087-3090
         if attention_mask is not None:

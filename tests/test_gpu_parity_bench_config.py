@@ -328,6 +328,8 @@ def test_text_encoder_cuda_graph_matches_eager():
         mask[0, :3] = 0
         got = model._encode_text(ids, mask)
         want = model._encode_text_eager(ids.to(DEV), mask.to(DEV))
+        hf = torch.nn.functional.linear(enc(input_ids=ids.to(DEV), attention_mask=mask.to(DEV)).last_hidden_state, *model.enc_to_dec_proj) * mask.to(DEV)[..., None]
+        assert (want - hf).abs().max().item() < 1e-5   # the device-built 4-D mask equals the library's own conversion of the 2-D mask
         assert got.shape == (2, 9, H)
         assert (got - want).abs().max().item() < 1e-5
         assert (got[0, :3] == 0).all()
