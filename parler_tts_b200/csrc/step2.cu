@@ -31,6 +31,8 @@
 #include "sample_core.cuh"
 #include "step.h"
 
+#include <cstdlib>
+
 namespace ptts {
 namespace cl {
 
@@ -250,7 +252,10 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   attention_decode_init_warp(attbars + 2 * warp, lane);
   cluster_arrive(); cluster_wait();   // every peer's mbarriers exist before any remote complete_tx
   cluster_arrive();                   // pre-arm: pairs with the first phase's "exchange buffers free" wait
-  const bool pf_on = !(p.dbg & 1);      // PTTS_DBG=1: no L2 prefetches (measurement switch)
+  // HBM -> L2 prefetches a layer ahead cost more than they bring here (1097 -> 1070 us per step without them: the shared-memory
+  // ring already runs two jobs = ~8 us ahead of its consumer, and every cp.async.bulk.prefetch.L2 is ~100 cycles of issue time
+  // inside a phase): off by default, PTTS_DBG=1 switches them on (profiles/r02_step2_phases.md)
+  const bool pf_on = (p.dbg & 1) != 0;
   const bool acq = (p.dbg & 32) != 0;   // PTTS_DBG=32: put the acquire fence back (grid_sync explains why it is not needed)
   unsigned* const bar_ctr = p.bar + (gen & 1u);
   unsigned bar_target = 0u;
@@ -823,7 +828,10 @@ static void cluster_launch_config(const StepParams& p, cudaLaunchConfig_t& cfg, 
   at[1].id = cudaLaunchAttributeCooperative;   // every CTA spins on the others: co-residency must be guaranteed
   at[1].val.cooperative = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 2;
+  // PTTS_STEP_COOP=0: cluster attribute only (Nsight Compute cannot launch a cooperative cluster grid; the 128 CTAs of an
+  // otherwise idle GPU are co-resident anyway -- profiling runs only)
+  static const bool coop = [] { const char* v = getenv("PTTS_STEP_COOP"); return !(v && v[0] == '0'); }();
+  cfg.numAttrs = coop ? 2 : 1;
 }
 
 // true when the 32 x 4 cluster grid can be co-resident on this device

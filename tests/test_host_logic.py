@@ -108,7 +108,23 @@ def _dist_worker(rank, world, port, q):
     audio = mine["encoder_outputs"][:, :2].clone()
     lengths = [1 + (int(v) % 2) for v in mine["encoder_outputs"][:, 0]]
     full = gather_ragged_audio(audio, lengths)
-    q.put((rank, ok_blob, mine["encoder_outputs"][:, 0].tolist(), mine["flag"], [a.tolist() for a in full]))
+    # broadcast_model_weights: rank 0 has loaded a checkpoint, rank 1 only constructed the model -- both must issue the SAME
+    # collectives (a rank that skipped `is not None` branches hung NCCL) and rank 1 must learn what was loaded
+    from types import SimpleNamespace
+    from parler_tts_b200.dist import broadcast_model_weights, shard_row_base
+    def fake(loaded):
+        fill = (lambda n, v: torch.full((n,), v, dtype=torch.uint8))
+        return SimpleNamespace(decoder=SimpleNamespace(engine=SimpleNamespace(blob=fill(64, 3 if loaded else 0))),
+                               audio_encoder=SimpleNamespace(blob=fill(32, 5 if loaded else 0), loaded=loaded),
+                               embed_prompts_weight=torch.full((4, 8), 2.0 if loaded else 0.0),
+                               enc_to_dec_proj=(torch.full((8, 6), 1.5 if loaded else 0.0), torch.full((8,), 0.5 if loaded else 0.0)),
+                               _side_loaded=loaded)
+    m = fake(rank == 0)
+    broadcast_model_weights(m)
+    ok_model = (bool((m.decoder.engine.blob == 3).all()) and bool((m.audio_encoder.blob == 5).all()) and bool((m.embed_prompts_weight == 2).all())
+                and bool((m.enc_to_dec_proj[0] == 1.5).all()) and bool((m.enc_to_dec_proj[1] == 0.5).all()) and m.audio_encoder.loaded and m._side_loaded)
+    assert shard_row_base(10, rank, world, 9) == (0 if rank == 0 else 45)
+    q.put((rank, ok_blob and ok_model, mine["encoder_outputs"][:, 0].tolist(), mine["flag"], [a.tolist() for a in full]))
     dist.destroy_process_group()
 
 

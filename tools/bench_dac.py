@@ -13,7 +13,7 @@ def main():
     sd = synth_dac_weights(cfg, dev)
     codes = torch.randint(0, 1024, (1, B, 9, T), device=dev)
     out = {}
-    for tc in ("1", "0"):
+    for tc in (("1",) if os.environ.get("PTTS_DAC_BENCH_TC_ONLY") == "1" else ("1", "0")):
         os.environ["PTTS_DAC_TC"] = tc
         m = DACModel(cfg, dev, torch.bfloat16).load_state_dict(sd)
         for _ in range(2): m.decode(codes, [None] * B)
