@@ -699,6 +699,8 @@ int ptts_dac_decode(const ptts_dac_config* cfg, const void* blob, void* workspac
       }
     }
     const int cl = C >> cfg->n_blocks;
+    if (final_conv_supported(cl) && env_flag("PTTS_DAC_FINAL_FAST", true))   // one thread per output sample (dac.cu)
+      return launch_final_conv_tanh(act, tpp(ti + 1), tpp(ti + 2), audio_out, cl, Tlen, B, st);
     ConvArgs f{};  // final conv (Cout = 1) + tanh on the already snake'd tensor: generic kernel
     f.x = act; f.w = tpp(ti + 1); f.bias = tpp(ti + 2); f.alpha = nullptr; f.res = nullptr; f.out = audio_out;
     f.Cin = cl; f.Cout = 1; f.Tin = Tlen; f.Tout = Tlen; f.q_count = Tlen;

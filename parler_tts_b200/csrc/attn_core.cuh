@@ -446,7 +446,7 @@ __device__ __forceinline__ void attention_decode_item_warp(const AttnArgs& p, in
 }
 
 // ---- decode attention on the tensor cores (bf16, MHA: one query head per K/V head) -----------------------------------------
-// Same contract, ring and merge protocol as attention_decode_item_warp, but a 16-key stage costs 16 mma.m16n8k16 instead of
+// Same contract, ring and merge protocol as attention_decode_item_warp, but 16 keys cost 16 mma.m16n8k16 instead of
 // ~250 scalar instructions (the SIMT sweep measured 37 ns per key per warp, latency-bound: profiles/r02_step2_phases.md):
 //   S = q K^T : A = the query in row 0 of an m16 x k16 fragment (4 k-steps over the 64 dims; rows 1..15 are zero),
 //               B = K rows straight from the staged tile with ldmatrix (keys are the n dimension) -> 2 n-tiles x 4 k-steps = 8 MMAs;
@@ -470,49 +470,45 @@ __device__ __forceinline__ uint32_t att_pack(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-constexpr int ATT_TC_CH = 16;   // keys per ring stage
-constexpr int ATT_TC_RING_BYTES = 2 * 2 * ATT_TC_CH * HD * 2;   // one warp's K/V ring: 8 KB
+constexpr int ATT_TC_CH = 32;   // keys per ring stage: one softmax / rescale chain per 32 keys (the chain, not the MMAs, bounds a stage)
+constexpr int ATT_TC_STAGE_BYTES = 2 * ATT_TC_CH * HD * 2;   // one stage: K rows then V rows (8 KB)
 
-// Requests the first two K/V stages of an item into the warp's ring (2 x 2 x 16 keys x 128 B at `ring`).  The cached rows do not
-// depend on the projection the same phase computes, so the cluster step kernel calls this right after its MMA loop -- a
-// microsecond or two before the attention itself starts -- and passes pre_issued = true below.
-__device__ __forceinline__ void attention_tc_issue_first(const AttnArgs& p, int b, int h, int pos, unsigned char* ring, uint64_t* bars, int lane,
+// Requests the FIRST K/V stage of an item into `ring0`.  The cached rows do not depend on the projection the same phase computes,
+// so the cluster step kernel calls this right after its MMA loop -- a microsecond or two before the attention itself starts --
+// and passes pre_issued = true below.
+__device__ __forceinline__ void attention_tc_issue_first(const AttnArgs& p, int b, int h, int pos, unsigned char* ring0, uint64_t* bars, int lane,
                                                          int part, int nparts) {
   constexpr int CH = ATT_TC_CH;
   const int n_cached = p.cross ? p.kv_len : pos;
-  const int n_chunks_all = (n_cached + CH - 1) / CH;
-  const int n_chunks = (n_chunks_all > part) ? (n_chunks_all - part + nparts - 1) / nparts : 0;
+  const int t0 = part * CH;
+  if (t0 >= n_cached) return;
+  const int n = (n_cached - t0 < CH) ? (n_cached - t0) : CH;
   const bf16* kc = reinterpret_cast<const bf16*>(p.kcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
   const bf16* vc = reinterpret_cast<const bf16*>(p.vcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
   __syncwarp();
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  for (int i = 0; i < 2 && i < n_chunks; i++) {
-    const int t0 = (part + nparts * i) * CH;
-    const int n = (n_cached - t0 < CH) ? (n_cached - t0) : CH;
-    const uint32_t bar = att_smem_u32(&bars[i]);
-    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * n * HD * 2)) : "memory");
-    __syncwarp();
-    if (lane < 2) {
-      const bf16* src = (lane == 0 ? kc : vc) + (size_t)t0 * HD;
-      bf16* dst = reinterpret_cast<bf16*>(ring) + (lane == 0 ? 0 : 2 * CH * HD) + i * CH * HD;
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(att_smem_u32(dst)), "l"(src), "r"((uint32_t)(n * HD * 2)), "r"(bar) : "memory");
-    }
+  const uint32_t bar = att_smem_u32(&bars[0]);
+  if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * n * HD * 2)) : "memory");
+  __syncwarp();
+  if (lane < 2) {
+    const bf16* src = (lane == 0 ? kc : vc) + (size_t)t0 * HD;
+    bf16* dst = reinterpret_cast<bf16*>(ring0) + (lane == 0 ? 0 : CH * HD);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(att_smem_u32(dst)), "l"(src), "r"((uint32_t)(n * HD * 2)), "r"(bar) : "memory");
   }
 }
 
-// ring: this warp's K/V stages ([2][16][64] K | [2][16][64] V, 16-byte aligned); fbuf: 192 floats (query, this step's key / value);
-// bars: this warp's two mbarriers.
-__device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p, int b, int h, int pos, unsigned char* ring, float* fbuf, uint64_t* bars,
-                                                              int lane, uint32_t& parity, int part, int nparts, float* xch, int pair_bar,
+// ring0 / ring1: this warp's two K/V stages ([32][64] K | [32][64] V each, 16-byte aligned, anywhere in shared memory);
+// fbuf: 192 floats (query, this step's key / value); bars: this warp's two mbarriers.
+__device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p, int b, int h, int pos, unsigned char* ring0, unsigned char* ring1, float* fbuf,
+                                                              uint64_t* bars, int lane, uint32_t& parity, int part, int nparts, float* xch, int pair_bar,
                                                               long long* prof = nullptr, bool pre_issued = false) {
   constexpr int CH = ATT_TC_CH;
-  constexpr int STAGE_ELEMS = CH * HD;
-  bf16* kst = reinterpret_cast<bf16*>(ring);                     // [2][CH][64] swizzled rows
-  bf16* vst = kst + 2 * STAGE_ELEMS;
-  float* qs = fbuf;                                              // [64] query (fp32 of the bf16 values)
-  float* kn = qs + HD;                                           // [64] this step's key   (self only)
-  float* vn = kn + HD;                                           // [64] this step's value (self only)
+  constexpr int NTS = CH / 8;     // score n-tiles per stage
+  constexpr int KPV = CH / 16;    // k16 steps of P V per stage
+  float* qs = fbuf;               // [64] query (fp32 of the bf16 values)
+  float* kn = qs + HD;            // [64] this step's key   (self only)
+  float* vn = kn + HD;            // [64] this step's value (self only)
   const bf16* __restrict__ rope_cos = reinterpret_cast<const bf16*>(p.rope_cos) + (size_t)pos * HD;
   const bf16* __restrict__ rope_sin = reinterpret_cast<const bf16*>(p.rope_sin) + (size_t)pos * HD;
   bf16* kc = reinterpret_cast<bf16*>(p.kcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
@@ -531,7 +527,7 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     __syncwarp();
     if (lane < 2) {
       const bf16* src = (lane == 0 ? kc : vc) + (size_t)t0 * HD;
-      bf16* dst = (lane == 0 ? kst : vst) + st * STAGE_ELEMS;
+      bf16* dst = reinterpret_cast<bf16*>(st ? ring1 : ring0) + (lane == 0 ? 0 : CH * HD);
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(att_smem_u32(dst)), "l"(src), "r"((uint32_t)(n * HD * 2)), "r"(bar) : "memory");
     }
@@ -547,12 +543,10 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     parity ^= (1u << st);
   };
 
-  if (!pre_issued) {
-    __syncwarp();
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (n_chunks > 0) issue(0);
-    if (n_chunks > 1) issue(1);
-  }
+  __syncwarp();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (!pre_issued && n_chunks > 0) issue(0);
+  if (n_chunks > 1) issue(1);   // (ring1 may alias buffers that were live when the first stage was requested early)
 
   // query (+ rotary), this step's K/V row (self): to the cache and to shared memory
   {
@@ -590,7 +584,7 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     qa2[ks] = (g == 0) ? att_pack(qs[16 * ks + 8 + 2 * t], qs[16 * ks + 8 + 2 * t + 1]) : 0u;
   }
   const int* km = p.key_mask ? p.key_mask + (size_t)b * p.mask_ld : nullptr;
-  if (prof != nullptr && lane == 0) prof[8] = clock64();   // set-up done (query, K/V append, first two stages requested)
+  if (prof != nullptr && lane == 0) prof[8] = clock64();   // set-up done (query, K/V append, stages requested)
   float m_run = -INFINITY, l_run = 0.f;
   float o[8][4];
 #pragma unroll
@@ -605,20 +599,21 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     const int t0 = (part + nparts * c) * CH;
     const int n = (n_cached - t0 < CH) ? (n_cached - t0) : CH;
     int mk = 1;
-    if (km != nullptr && lane < CH && t0 + lane < p.mask_len && t0 + lane < n_cached) mk = km[t0 + lane];
+    if (km != nullptr && t0 + lane < p.mask_len && t0 + lane < n_cached) mk = km[t0 + lane];   // (CH == 32: one key per lane)
     wait_stage(st);
     const uint32_t mword = __ballot_sync(0xffffffffu, mk != 0);
-    const uint32_t kbase = att_smem_u32(kst + st * STAGE_ELEMS), vbase = att_smem_u32(vst + st * STAGE_ELEMS);
+    bf16* stage = reinterpret_cast<bf16*>(st ? ring1 : ring0);
+    const uint32_t kbase = att_smem_u32(stage), vbase = att_smem_u32(stage + CH * HD);
     if (n < CH) {  // last, partial stage: the copy filled n rows; whatever the rest of the V stage holds must not meet the MMA
       // (probability 0 x a stale NaN bit pattern is NaN); stale K rows only produce scores that are replaced by -inf below
       for (int i = lane; i < (CH - n) * 8; i += 32)
-        *reinterpret_cast<uint4*>(vst + st * STAGE_ELEMS + (size_t)(n + (i >> 3)) * HD + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(stage + CH * HD + (size_t)(n + (i >> 3)) * HD + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
       __syncwarp();
     }
-    // ---- scores of the 16 keys ----
-    float s[2][4];
+    // ---- scores of the 32 keys: 4 n-tiles x 4 k-steps ----
+    float s[NTS][4];
 #pragma unroll
-    for (int nt = 0; nt < 2; nt++) {
+    for (int nt = 0; nt < NTS; nt++) {
 #pragma unroll
       for (int e = 0; e < 4; e++) s[nt][e] = 0.f;
 #pragma unroll
@@ -630,39 +625,43 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
       }
     }
     // lanes 0..3 (g == 0): s[nt][0], s[nt][1] = keys 8 nt + 2 t, 8 nt + 2 t + 1
-    float sv[4];
+    float sv[2 * NTS];
+    float cmax = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < 2; nt++)
+    for (int nt = 0; nt < NTS; nt++)
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int key = 8 * nt + 2 * t + e;
         sv[2 * nt + e] = (g == 0 && key < n && ((mword >> key) & 1u)) ? s[nt][e] * p.scale : -INFINITY;
+        cmax = fmaxf(cmax, sv[2 * nt + e]);
       }
-    float cmax = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
     cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 1));
     cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 2));
     cmax = __shfl_sync(0xffffffffu, cmax, 0);          // the g == 0 quad's maximum, warp-uniform
     const float m_new = fmaxf(m_run, cmax);
     if (m_new != -INFINITY) {                          // (warp-uniform) otherwise every key so far is masked
       const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
-      float pe[4], lsum = 0.f;
+      float pe[2 * NTS], lsum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; i++) { pe[i] = expf(sv[i] - m_new); lsum += pe[i]; }   // exactly 0 for masked / out-of-range keys and lanes >= 4
+      for (int i = 0; i < 2 * NTS; i++) { pe[i] = expf(sv[i] - m_new); lsum += pe[i]; }   // exactly 0 for masked / out-of-range keys and lanes >= 4
       lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
       lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
       l_run = l_run * corr + lsum;                     // meaningful on lanes 0..3
       m_run = m_new;
-      const uint32_t pa0 = att_pack(pe[0], pe[1]), pa2 = att_pack(pe[2], pe[3]);   // probabilities rounded to bf16 (zeros off row 0)
 #pragma unroll
       for (int j = 0; j < 8; j++) { o[j][0] *= corr; o[j][1] *= corr; }
 #pragma unroll
-      for (int jp = 0; jp < 4; jp++) {                 // dims 16 jp .. 16 jp + 15: n-tiles 2 jp, 2 jp + 1
-        uint32_t vb[4];
-        // matrices: (n-tile 2jp, keys 0-7), (2jp, keys 8-15), (2jp+1, keys 0-7), (2jp+1, keys 8-15); rows = keys, transposed on load
-        const int key = (mi & 1) * 8 + r8, chunk = 2 * jp + (mi >> 1);
-        att_ldsm4_t(vb, vbase + (uint32_t)(key * 128 + ((chunk ^ r8) << 4)));
-        att_mma(o[2 * jp], pa0, 0u, pa2, 0u, vb[0], vb[1]);
-        att_mma(o[2 * jp + 1], pa0, 0u, pa2, 0u, vb[2], vb[3]);
+      for (int kp = 0; kp < KPV; kp++) {               // keys 16 kp .. 16 kp + 15: probabilities rounded to bf16 (zeros off row 0)
+        const uint32_t pa0 = att_pack(pe[4 * kp], pe[4 * kp + 1]), pa2 = att_pack(pe[4 * kp + 2], pe[4 * kp + 3]);
+#pragma unroll
+        for (int jp = 0; jp < 4; jp++) {               // dims 16 jp .. 16 jp + 15: n-tiles 2 jp, 2 jp + 1
+          uint32_t vb[4];
+          // matrices: (n-tile 2jp, keys 0-7), (2jp, keys 8-15), (2jp+1, keys 0-7), (2jp+1, keys 8-15) of this k-step; rows = keys, transposed on load
+          const int key = 16 * kp + (mi & 1) * 8 + r8, chunk = 2 * jp + (mi >> 1);
+          att_ldsm4_t(vb, vbase + (uint32_t)(key * 128 + ((chunk ^ r8) << 4)));
+          att_mma(o[2 * jp], pa0, 0u, pa2, 0u, vb[0], vb[1]);
+          att_mma(o[2 * jp + 1], pa0, 0u, pa2, 0u, vb[2], vb[3]);
+        }
       }
     }
     if (c + 2 < n_chunks) {

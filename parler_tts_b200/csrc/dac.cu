@@ -187,4 +187,57 @@ int pack_conv(const void* src, int src_dtype, void* dst, int dst_dtype, int d0, 
 
 // audio [B][T][1] is already [B, 1, T] contiguous: nothing to transpose for the final layer.
 
+
+// ---- output convolution: Conv1d(C -> 1, k = 7) + tanh on the channels-last, already snake'd tensor ----------------------------
+// The generic tile kernel above computes a 64 x 64 output tile: with ONE output channel 63/64 of its FMAs are wasted and it took
+// 2.5 ms for 32 x 57 frames (11 ms at the bench's 248 frames: a third of the whole decode; profiles/r02_launches.md).
+// Here one thread owns one output sample: the 128 + 6 input rows of a block are staged in shared memory (row pitch padded to
+// C + 8 elements so that 8 consecutive threads' 16-byte reads hit 8 different bank groups), weights [7][C] as fp32.
+// bf16 inputs, fp32 accumulation in tap-major / channel order, one rounding of acc + bias, tanh, one rounding (torch's ops).
+constexpr int FC_T = 128;   // outputs per block
+__global__ void __launch_bounds__(FC_T) final_conv_tanh_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ bias,
+                                                               bf16* __restrict__ out, int C, int T) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  const int pitch = C + 8;                                   // elements
+  bf16* xs = reinterpret_cast<bf16*>(fsm);                   // [FC_T + 6][pitch]
+  float* ws = reinterpret_cast<float*>(fsm + (size_t)(FC_T + 6) * pitch * 2);   // [7][C]
+  const int b = blockIdx.y, t0 = blockIdx.x * FC_T, tid = threadIdx.x;
+  const bf16* xb = x + (size_t)b * T * C;
+  const int vec_per_row = C / 8;
+  for (int e = tid; e < (FC_T + 6) * vec_per_row; e += FC_T) {
+    const int r = e / vec_per_row, c = e - r * vec_per_row;
+    const int t = t0 - 3 + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);                    // zero padding outside [0, T)
+    if (t >= 0 && t < T) v = *reinterpret_cast<const uint4*>(xb + (size_t)t * C + c * 8);
+    *reinterpret_cast<uint4*>(xs + (size_t)r * pitch + c * 8) = v;
+  }
+  for (int e = tid; e < 7 * C; e += FC_T) ws[e] = __bfloat162float(w[e]);   // packed [tap][Cin][Cout = 1]
+  __syncthreads();
+  const int t = t0 + tid;
+  if (t >= T) return;
+  float acc = 0.f;
+  for (int j = 0; j < 7; j++) {
+    const bf16* row = xs + (size_t)(tid + j) * pitch;
+    const float* wj = ws + j * C;
+    for (int c = 0; c < C; c += 8) {
+      float v[8];
+      load8(row + c, v);
+#pragma unroll
+      for (int e = 0; e < 8; e++) acc = fmaf(v[e], wj[c + e], acc);
+    }
+  }
+  const float y = DT<bf16>::rnd(acc + __bfloat162float(bias[0]));
+  out[(size_t)b * T + t] = __float2bfloat16_rn(tanhf(y));
+}
+
+bool final_conv_supported(int C) { return C % 8 == 0 && C <= 512; }
+int launch_final_conv_tanh(const void* x, const void* w, const void* bias, void* out, int C, int T, int B, cudaStream_t st) {
+  const size_t smem = (size_t)(FC_T + 6) * (C + 8) * 2 + (size_t)7 * C * 4;
+  static bool attr = false;
+  if (!attr) { PTTS_CHECK_CUDA(cudaFuncSetAttribute(final_conv_tanh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+  final_conv_tanh_kernel<<<dim3((T + FC_T - 1) / FC_T, B), FC_T, smem, st>>>((const bf16*)x, (const bf16*)w, (const bf16*)bias, (bf16*)out, C, T);
+  PTTS_LAUNCH_CHECK();
+  return PTTS_OK;
+}
+
 }  // namespace ptts

@@ -30,6 +30,9 @@ int pack_conv(const void* src, int src_dtype, void* dst, int dst_dtype, int d0, 
 bool conv_tc_supported(int Cin, int Cout);
 int launch_conv_tc(const ConvArgs& a, const void* w_kmajor, int taps_total, const void* alpha_next, void* out_raw, void* out_act, int B, cudaStream_t st);
 int pack_conv_kmajor(const void* src, int src_dtype, void* dst, int d0, int d1, int k, int transposed, cudaStream_t st);
+// output convolution (C -> 1, k = 7) + tanh on the already snake'd channels-last tensor, bf16 (dac.cu)
+bool final_conv_supported(int C);
+int launch_final_conv_tanh(const void* x, const void* w, const void* bias, void* out, int C, int T, int B, cudaStream_t st);
 
 enum { DK_PLAIN = 0, DK_CONV = 1, DK_CONVT = 2 };
 struct DacTensor {

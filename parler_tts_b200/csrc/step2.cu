@@ -370,7 +370,6 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     const char* lb = blob + p.layer0 + p.layer_stride * l;
     const bool rowpart = (sub == PH_QKV || sub == PH_QC);
     const bool has_ln = (sub == PH_QKV || sub == PH_QC || sub == PH_FC1);
-    const int MT = rowpart ? 1 : 2;                                  // m16 tiles (the head phases see one row half)
     const int q = (sub == PH_QKV) ? 6 : (sub == PH_QC ? 2 : (sub == PH_FC1 ? qe : 1));   // n-tiles per warp
     const int Nc = 4 * q * 8;                                        // features of this cluster in this phase
     const int KT = (sub == PH_FC2 ? KsF : Ks) >> 5;                  // k32 tiles of this CTA's slice; a warp reduces half of them
@@ -432,8 +431,6 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     if (has_ln && tid < (rowpart ? Nc : 8 * q)) { cvec[tid] = cv1; cvec[256 + tid] = cv2; }   // read in the epilogue, several barriers later
     __syncthreads();  // activation slice and weight buffer(s) are dead
     if (lane == 0) {  // asynchronous requests, one or two per warp so that no single thread holds the CTA back
-      if (warp == 1 && sub != PH_QC) for (int i = 0; i < njobs; i++) issue_weight_job(j0 + i + 2);   // refill the ring two jobs ahead
-      // (q_cross holds fc1's weights back until its attention is done: the K/V rings live in that buffer meanwhile)
       for (int i = 0; i < njobs; i++) prefetch_weight_job_part(j0 + i + JOBS_PER_LAYER, warp);  // same job, next layer (or lm heads) -> L2
       if (sub == PH_QKV && warp == 2 && l + 1 < p.L) {   // next layer's folded-LN vectors: every CTA pulls a 1/grid share into L2
         const int64_t c_bytes = p.c_fc1 + (int64_t)2 * F * 4 - p.c_qkv;
@@ -444,51 +441,9 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       if (sub == PH_O && l + 1 < p.L) prefetch_kv_part(l + 1, false, warp);
       if (sub == PH_OC && l + 1 < p.L) prefetch_kv_part(l + 1, true, warp);
     }
-    // The attention of the head phases: build its arguments and request the first two K/V stages of this warp's item now.
-    // The rings live in the weight ring's idle space (the phase's own weights are dead, the next jobs fill only the heads of the
-    // buffers), so they alias nothing the exchange uses and can fill while it runs.
-    AttnArgs att{};
-    int att_b = B;
-    unsigned char* att_ring = nullptr; float* att_f = nullptr; float* att_xch = nullptr;
-    if (rowpart) {
-      att.ctrl = nullptr; att.B = B; att.nh = p.nh; att.nkv = p.nh; att.q_len = 1;
-      att.past_from_ctrl = 0; att.past_len = pos; att.prefix = p.P;
-      att.rope = p.rope; att.rope_cos = blob + p.rope_cos; att.rope_sin = blob + p.rope_sin; att.scale = p.scale;
-      const bf16* qkv_s = reinterpret_cast<const bf16*>(Rg + QKV_OFF);
-      const int row_base = 16 * half + 4 * rank;
-      // row b = row_base + i, head: q at qkv_s[i][0..63] (k at +64, v at +128 for the self phase)
-      const bf16* qbase = qkv_s - (size_t)row_base * Nc - (size_t)head * HD;
-      att.q = qbase; att.ldq = Nc; att.q_col0 = 0;
-      att.ldo = pitch;   // attn image: row b, head h -> slice h / 4, column (h % 4) * 64
-      att.out = a_img + (size_t)(head >> 2) * x_slice_elems + (head & 3) * HD - (size_t)head * HD;
-      unsigned char* wb0 = smem + HDR;   // the two weight ring buffers
-      if (sub == PH_QKV) {
-        att.knew = qbase; att.vnew = qbase; att.ldkv = Nc; att.k_col0 = HD; att.v_col0 = 2 * HD;
-        char* kc = p.self_kv + p.self_layer_stride * l;
-        att.kcache = kc; att.vcache = kc + (size_t)B * p.nh * p.Tmax * HD * 2;
-        att.kv_b_stride = (int64_t)p.nh * p.Tmax * HD; att.kv_h_stride = (int64_t)p.Tmax * HD; att.kv_t_stride = HD;
-        att.key_mask = p.prompt_mask; att.mask_len = p.P; att.mask_ld = p.P;
-        att.cross = 0; att.kv_len = 0; att.kv_capacity = p.Tmax;
-        // out-proj's 16 KB go to the head of buffer (j0+2)&1, q_cross's 32 KB to the head of the other one
-        unsigned char* bB = wb0 + ((j0 + 2) & 1) * WB_BYTES; unsigned char* bC = wb0 + ((j0 + 3) & 1) * WB_BYTES;
-        att_ring = warp < 6 ? bB + 16384 + warp * ATT_TC_RING_BYTES : bC + 32768 + (warp - 6) * ATT_TC_RING_BYTES;
-        att_xch = reinterpret_cast<float*>(bC + 49152) + (warp >> 1) * 128;
-      } else {
-        att.knew = nullptr; att.vnew = nullptr;
-        char* ck = p.cross_kv + p.cross_layer_stride * l;
-        att.kcache = ck; att.vcache = ck + (size_t)B * p.nh * p.S * HD * 2;
-        att.kv_b_stride = (int64_t)p.nh * p.S * HD; att.kv_h_stride = (int64_t)p.S * HD; att.kv_t_stride = HD;
-        att.key_mask = p.enc_mask; att.mask_len = p.S; att.mask_ld = p.S;
-        att.cross = 1; att.kv_len = p.S; att.kv_capacity = p.S;
-        // this phase's own (dead) weight buffer holds the rings; cross out-proj's 16 KB sit at the head of the other one
-        att_ring = wb0 + (j0 & 1) * WB_BYTES + warp * ATT_TC_RING_BYTES;
-        att_xch = reinterpret_cast<float*>(wb0 + ((j0 + 1) & 1) * WB_BYTES + 16384) + (warp >> 1) * 128;
-      }
-      att_f = reinterpret_cast<float*>(Rg + 65536) + warp * 192;   // query / new key / new value: a corner of R the exchange never uses
-      att_b = row_base + (warp >> 1);
-      if (att_b < B && !(p.dbg & 16)) attention_tc_issue_first(att, att_b, head, pos, att_ring, attbars + 2 * warp, lane, warp & 1, 2);
-    }
+    prof_mark(prof, 12);
     cluster_wait();  // every peer is past its previous epilogue: my send blocks have been read, its receive slots are free
+    prof_mark(prof, 13);
 
     // ---- exchange: each warp stages its partial block in shared memory and ships it with ONE cp.async.bulk per destination
     // (shared::cta -> shared::cluster, complete_tx on the destination's mbarrier); no CTA-wide synchronisation on the way ----
@@ -539,6 +494,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         }
       }
       __syncwarp();
+      prof_mark(prof, 14);
       if (!rowpart) {
         if (lane == 0) {
           fence_proxy_async_smem();
@@ -549,6 +505,63 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         bulk_s2peer(mapa(s32(recv + (size_t)(8 * rank + warp) * blk), (uint32_t)lane), mine + (size_t)lane * blk, (uint32_t)blk, mapa(s32(xbar), (uint32_t)lane));
       }
     }
+    // Requests that are not on the critical path go out now, while the partial sums travel: the weight ring's refill (two jobs
+    // ahead; q_cross holds fc1's weights back until its attention is done, the K/V rings live in that buffer meanwhile) and, for
+    // the head phases, the first K/V stage of this warp's attention item.  The rings live in the weight ring's idle space (the
+    // phase's own weights are dead, the next jobs fill only the heads of the buffers), so they alias nothing the exchange uses.
+    if (warp == 1 && lane == 0 && sub != PH_QC) for (int i = 0; i < njobs; i++) issue_weight_job(j0 + i + 2);
+    AttnArgs att{};
+    int att_b = B;
+    unsigned char* att_ring = nullptr; unsigned char* att_ring1 = nullptr; float* att_f = nullptr; float* att_xch = nullptr;
+    if (rowpart) {
+      att.ctrl = nullptr; att.B = B; att.nh = p.nh; att.nkv = p.nh; att.q_len = 1;
+      att.past_from_ctrl = 0; att.past_len = pos; att.prefix = p.P;
+      att.rope = p.rope; att.rope_cos = blob + p.rope_cos; att.rope_sin = blob + p.rope_sin; att.scale = p.scale;
+      const bf16* qkv_s = reinterpret_cast<const bf16*>(Rg + QKV_OFF);
+      const int row_base = 16 * half + 4 * rank;
+      // row b = row_base + i, head: q at qkv_s[i][0..63] (k at +64, v at +128 for the self phase)
+      const bf16* qbase = qkv_s - (size_t)row_base * Nc - (size_t)head * HD;
+      att.q = qbase; att.ldq = Nc; att.q_col0 = 0;
+      att.ldo = pitch;   // attn image: row b, head h -> slice h / 4, column (h % 4) * 64
+      att.out = a_img + (size_t)(head >> 2) * x_slice_elems + (head & 3) * HD - (size_t)head * HD;
+      unsigned char* wb0 = smem + HDR;   // the two weight ring buffers
+      if (sub == PH_QKV) {
+        att.knew = qbase; att.vnew = qbase; att.ldkv = Nc; att.k_col0 = HD; att.v_col0 = 2 * HD;
+        char* kc = p.self_kv + p.self_layer_stride * l;
+        att.kcache = kc; att.vcache = kc + (size_t)B * p.nh * p.Tmax * HD * 2;
+        att.kv_b_stride = (int64_t)p.nh * p.Tmax * HD; att.kv_h_stride = (int64_t)p.Tmax * HD; att.kv_t_stride = HD;
+        att.key_mask = p.prompt_mask; att.mask_len = p.P; att.mask_ld = p.P;
+        att.cross = 0; att.kv_len = 0; att.kv_capacity = p.Tmax;
+        // out-proj's 16 KB go to the head of buffer (j0+2)&1, q_cross's 32 KB to the head of the other one.  Stage 0 of every warp
+        // (requested now) sits in those buffers' tails; stage 1 (requested when the attention starts) in what the exchange has
+        // released by then: the receive slots [34 KB, 58 KB) and the activation slice [0, 8 KB) of R, the gap behind the query
+        // scratch [71 KB, 87 KB), and the rest of the q_cross buffer's tail.
+        unsigned char* bB = wb0 + ((j0 + 2) & 1) * WB_BYTES; unsigned char* bC = wb0 + ((j0 + 3) & 1) * WB_BYTES;
+        att_ring = warp < 6 ? bB + 16384 + warp * ATT_TC_STAGE_BYTES : bC + 32768 + (warp - 6) * ATT_TC_STAGE_BYTES;
+        att_ring1 = warp < 3 ? Rg + 34048 + warp * ATT_TC_STAGE_BYTES : (warp < 5 ? Rg + 72704 + (warp - 3) * ATT_TC_STAGE_BYTES
+                  : (warp == 5 ? Rg : bC + 49152 + (warp - 6) * ATT_TC_STAGE_BYTES));
+        att_xch = reinterpret_cast<float*>(Rg + 59648) + (warp >> 1) * 128;
+      } else {
+        att.knew = nullptr; att.vnew = nullptr;
+        char* ck = p.cross_kv + p.cross_layer_stride * l;
+        att.kcache = ck; att.vcache = ck + (size_t)B * p.nh * p.S * HD * 2;
+        att.kv_b_stride = (int64_t)p.nh * p.S * HD; att.kv_h_stride = (int64_t)p.S * HD; att.kv_t_stride = HD;
+        att.key_mask = p.enc_mask; att.mask_len = p.S; att.mask_ld = p.S;
+        att.cross = 1; att.kv_len = p.S; att.kv_capacity = p.S;
+        // this phase's own (dead) weight buffer holds stage 0 of every warp; cross out-proj's 16 KB sit at the head of the other one.
+        // Stage 1 (descriptions longer than 64 positions): R behind the exchange buffers, the gap behind the query scratch, and
+        // the cross out-proj buffer's tail.
+        unsigned char* bD = wb0 + ((j0 + 1) & 1) * WB_BYTES;
+        att_ring = wb0 + (j0 & 1) * WB_BYTES + warp * ATT_TC_STAGE_BYTES;
+        att_ring1 = warp < 4 ? Rg + 28672 + warp * ATT_TC_STAGE_BYTES : (warp < 6 ? Rg + 72704 + (warp - 4) * ATT_TC_STAGE_BYTES
+                  : bD + 16384 + (warp - 6) * ATT_TC_STAGE_BYTES);
+        att_xch = reinterpret_cast<float*>(bD + 32768) + (warp >> 1) * 128;
+      }
+      att_f = reinterpret_cast<float*>(Rg + 65536) + warp * 192;   // query / new key / new value: a corner of R the exchange never uses
+      att_b = row_base + (warp >> 1);
+      if (att_b < B && !(p.dbg & 16)) attention_tc_issue_first(att, att_b, head, pos, att_ring, attbars + 2 * warp, lane, warp & 1, 2);
+    }
+    prof_mark(prof, 15);
     mbar_wait(xbar, par_x, 2);
     par_x ^= 1u;
     prof_mark(prof, 3);
@@ -638,11 +651,11 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       if (att_b < B) {
         if (p.dbg & 16) {  // A/B: the SIMT sweep (its ring layout: K/V stages then 192 floats, inside the R region)
           unsigned char* region = Rg + (size_t)warp * attn_decode_smem_per_warp<bf16, ATT_CH>();
-          float* xr = reinterpret_cast<float*>(Rg + (size_t)V * attn_decode_smem_per_warp<bf16, ATT_CH>()) + (warp >> 1) * 128;
+          float* xr = reinterpret_cast<float*>(Rg + 73728) + (warp >> 1) * 128;
           attention_decode_item_warp<bf16, ATT_CH>(att, att_b, head, pos, region, attbars + 2 * warp, lane, att_parity, warp & 1, 2, xr, (warp >> 1) + 1);
         } else {
-          attention_decode_item_warp_tc(att, att_b, head, pos, att_ring, att_f, attbars + 2 * warp, lane, att_parity, warp & 1, 2, att_xch, (warp >> 1) + 1,
-                                        warp == 0 ? prof : nullptr, true);
+          attention_decode_item_warp_tc(att, att_b, head, pos, att_ring, att_ring1, att_f, attbars + 2 * warp, lane, att_parity, warp & 1, 2, att_xch,
+                                        (warp >> 1) + 1, warp == 0 ? prof : nullptr, true);
         }
       }
       prof_mark(prof, 5);

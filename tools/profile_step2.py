@@ -52,9 +52,10 @@ for sub in range(6):
     work = us(rows[:, 6] - rows[:, 0])
     out[names[sub]] = dict(work=work.mean(), barrier=barr.mean(), wait=wait.mean(), mma=mma.mean(), exch=exch.mean(), epi=epi.mean(), attn=attn.mean())
     tot_l += work.mean() + barr.mean()
-    extra = ""
+    extra = (f"  [exch: pre {us(rows[:, 12] - rows[:, 2]).mean():.2f} clwait {us(rows[:, 13] - rows[:, 12]).mean():.2f} stage {us(rows[:, 14] - rows[:, 13]).mean():.2f}"
+             f" issue {us(rows[:, 15] - rows[:, 14]).mean():.2f} wait {us(rows[:, 3] - rows[:, 15]).mean():.2f}]")
     if sub in (0, 2):   # attention internals (warp 0): cluster sync + set-up | ring sweep | own key + merge | store
-        extra = (f"  [attn: setup {us(rows[:, 8] - rows[:, 4]).mean():.2f} sweep {us(rows[:, 9] - rows[:, 8]).mean():.2f} ({rows[:, 11].mean():.1f} chunks)"
+        extra += (f"  [attn: setup {us(rows[:, 8] - rows[:, 4]).mean():.2f} sweep {us(rows[:, 9] - rows[:, 8]).mean():.2f} ({rows[:, 11].mean():.1f} chunks)"
                  f" merge {us(rows[:, 10] - rows[:, 9]).mean():.2f} store {us(rows[:, 5] - rows[:, 10]).mean():.2f}]")
     print(f"{names[sub]:20s} work {work.mean():6.2f}  barrier {barr.mean():5.2f} | wait {wait.mean():5.2f}  mma {mma.mean():5.2f}  exch {exch.mean():5.2f}"
           f"  epi {epi.mean():5.2f}  attn {attn.mean():5.2f}{extra}")
