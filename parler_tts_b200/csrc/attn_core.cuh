@@ -485,8 +485,8 @@ __device__ __forceinline__ void attention_tc_issue_first(const AttnArgs& p, int 
   const int n = (n_cached - t0 < CH) ? (n_cached - t0) : CH;
   const bf16* kc = reinterpret_cast<const bf16*>(p.kcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
   const bf16* vc = reinterpret_cast<const bf16*>(p.vcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
+  // (no proxy fence: the stage was last written by the async proxy and read with generic loads; see step2.cu issue_weight_job)
   __syncwarp();
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   const uint32_t bar = att_smem_u32(&bars[0]);
   if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * n * HD * 2)) : "memory");
   __syncwarp();
@@ -543,8 +543,11 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     parity ^= (1u << st);
   };
 
+  // The stages are written by bulk copies (async proxy) and read with ldmatrix / generic loads: refilling one is a write-after-read
+  // across proxies, which needs no proxy fence -- and fence.proxy.async would wait for every bulk copy the CTA has in flight
+  // (the 64 KB weight jobs of the step kernel: ~0.5 us each time).  The only generic WRITE into a stage (zero-filling the tail of
+  // an item's last, partial stage) is followed by the device-wide barrier's fence before the stage is refilled.
   __syncwarp();
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (!pre_issued && n_chunks > 0) issue(0);
   if (n_chunks > 1) issue(1);   // (ring1 may alias buffers that were live when the first stage was requested early)
 
@@ -666,7 +669,6 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     }
     if (c + 2 < n_chunks) {
       __syncwarp();
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       issue(c + 2);
     }
   }

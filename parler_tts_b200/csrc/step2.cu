@@ -270,7 +270,10 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   auto issue_weight_job = [&](int j) {  // ONE thread
     const char* src; uint32_t bytes;
     if (!weight_job(p, j, cta, rank, src, bytes)) return;
-    fence_proxy_async_smem();
+    // No proxy fence here: the ring buffers are only ever WRITTEN through the async proxy (weights, K/V stages) and read with
+    // generic loads -- a write-after-read across proxies needs none -- and fence.proxy.async waits for every bulk copy the CTA has
+    // in flight (it cost ~0.5 us wherever one sat behind a 64 KB weight copy).  The one generic-written corner (the attention
+    // merge scratch of the q_cross phase) is covered by the fence thread 0 executes at every device-wide barrier (request_slice).
     mbar_expect_tx(&wbar[j & 1], bytes);
     bulk_g2s(smem + HDR + (j & 1) * WB_BYTES, src, bytes, &wbar[j & 1]);
   };
