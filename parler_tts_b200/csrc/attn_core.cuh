@@ -470,6 +470,12 @@ __device__ __forceinline__ uint32_t att_pack(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+__device__ __forceinline__ float att_ex2(float x) {   // 2^x, 2 ulp; ex2(-inf) = +0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int ATT_TC_CH = 32;   // keys per ring stage: one softmax / rescale chain per 32 keys (the chain, not the MMAs, bounds a stage)
 constexpr int ATT_TC_STAGE_BYTES = 2 * ATT_TC_CH * HD * 2;   // one stage: K rows then V rows (8 KB)
 
@@ -543,6 +549,13 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     parity ^= (1u << st);
   };
 
+  const int* km = p.key_mask ? p.key_mask + (size_t)b * p.mask_ld : nullptr;
+  auto load_mask = [&](int c) -> int {   // one key per lane (CH == 32); requested one stage ahead of its use
+    const int t0 = (part + nparts * c) * CH;
+    return (km != nullptr && c < n_chunks && t0 + lane < p.mask_len && t0 + lane < n_cached) ? km[t0 + lane] : 1;
+  };
+  int mk_next = load_mask(0);   // (first use: the ballot after the first stage has landed)
+
   // The stages are written by bulk copies (async proxy) and read with ldmatrix / generic loads: refilling one is a write-after-read
   // across proxies, which needs no proxy fence -- and fence.proxy.async would wait for every bulk copy the CTA has in flight
   // (the 64 KB weight jobs of the step kernel: ~0.5 us each time).  The only generic WRITE into a stage (zero-filling the tail of
@@ -579,16 +592,19 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
   }
   __syncwarp();
   const int g = lane >> 2, t = lane & 3;
-  // A fragments of the query: row 0 only (lanes 0..3): k-step ks covers dims 16 ks .. 16 ks + 15
+  // A fragments of the query: the SAME row in fragment rows 0..3 (lanes g < 4); k-step ks covers dims 16 ks .. 16 ks + 15.
+  // Every row g < 4 then receives the scores of all 32 keys of a stage, and lane (g, t) takes the two of n-tile g: the softmax
+  // arithmetic (mask, exp2, sums) is spread over 16 lanes instead of repeated 8 times on 4, and row g of the P V product
+  // accumulates the keys of n-tile g only -- the four partial rows are added once per item, after the sweep.
   uint32_t qa0[4], qa2[4];
 #pragma unroll
   for (int ks = 0; ks < 4; ks++) {
-    qa0[ks] = (g == 0) ? att_pack(qs[16 * ks + 2 * t], qs[16 * ks + 2 * t + 1]) : 0u;
-    qa2[ks] = (g == 0) ? att_pack(qs[16 * ks + 8 + 2 * t], qs[16 * ks + 8 + 2 * t + 1]) : 0u;
+    qa0[ks] = (g < 4) ? att_pack(qs[16 * ks + 2 * t], qs[16 * ks + 2 * t + 1]) : 0u;
+    qa2[ks] = (g < 4) ? att_pack(qs[16 * ks + 8 + 2 * t], qs[16 * ks + 8 + 2 * t + 1]) : 0u;
   }
-  const int* km = p.key_mask ? p.key_mask + (size_t)b * p.mask_ld : nullptr;
   if (prof != nullptr && lane == 0) prof[8] = clock64();   // set-up done (query, K/V append, stages requested)
-  float m_run = -INFINITY, l_run = 0.f;
+  const float scale_l2 = p.scale * 1.4426950408889634f;   // scores and running maximum live in the log2 domain (ex2.approx)
+  float m_run = -INFINITY, l_run = 0.f;                    // l_run: THIS lane's share of the denominator until the final reduction
   float o[8][4];
 #pragma unroll
   for (int j = 0; j < 8; j++)
@@ -596,15 +612,17 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     for (int e = 0; e < 4; e++) o[j][e] = 0.f;
   // ldmatrix lane addressing inside a stage: matrix mi = lane >> 3, row r = lane & 7 (16-byte chunk c of key row k at (c ^ (k & 7)) * 16)
   const int mi = lane >> 3, r8 = lane & 7;
+  const int my_key = (8 * g + 2 * t) & 31;   // (g < 4) this lane's two keys inside a stage
 
   for (int c = 0; c < n_chunks; c++) {
     const int st = c & 1;
     const int t0 = (part + nparts * c) * CH;
     const int n = (n_cached - t0 < CH) ? (n_cached - t0) : CH;
-    int mk = 1;
-    if (km != nullptr && t0 + lane < p.mask_len && t0 + lane < n_cached) mk = km[t0 + lane];   // (CH == 32: one key per lane)
+    const int mk = mk_next;
+    mk_next = load_mask(c + 1);
     wait_stage(st);
-    const uint32_t mword = __ballot_sync(0xffffffffu, mk != 0);
+    uint32_t vword = __ballot_sync(0xffffffffu, mk != 0);
+    if (n < CH) vword &= (1u << n) - 1u;
     bf16* stage = reinterpret_cast<bf16*>(st ? ring1 : ring0);
     const uint32_t kbase = att_smem_u32(stage), vbase = att_smem_u32(stage + CH * HD);
     if (n < CH) {  // last, partial stage: the copy filled n rows; whatever the rest of the V stage holds must not meet the MMA
@@ -627,35 +645,27 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
         att_mma(s[nt], qa0[2 * half + 1], 0u, qa2[2 * half + 1], 0u, kb[2], kb[3]);
       }
     }
-    // lanes 0..3 (g == 0): s[nt][0], s[nt][1] = keys 8 nt + 2 t, 8 nt + 2 t + 1
-    float sv[2 * NTS];
-    float cmax = -INFINITY;
+    // rows g < 4 all hold s[nt][0], s[nt][1] = keys 8 nt + 2 t, 8 nt + 2 t + 1; lane (g, t) keeps n-tile g
+    static_assert(NTS == 4, "one score n-tile per fragment row 0..3");
+    const float r0 = (g & 2) ? ((g & 1) ? s[3][0] : s[2][0]) : ((g & 1) ? s[1][0] : s[0][0]);
+    const float r1 = (g & 2) ? ((g & 1) ? s[3][1] : s[2][1]) : ((g & 1) ? s[1][1] : s[0][1]);
+    const float sv0 = (g < 4 && ((vword >> my_key) & 1u)) ? r0 * scale_l2 : -INFINITY;
+    const float sv1 = (g < 4 && ((vword >> my_key) & 2u)) ? r1 * scale_l2 : -INFINITY;
+    float cmax = fmaxf(sv0, sv1);
 #pragma unroll
-    for (int nt = 0; nt < NTS; nt++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int key = 8 * nt + 2 * t + e;
-        sv[2 * nt + e] = (g == 0 && key < n && ((mword >> key) & 1u)) ? s[nt][e] * p.scale : -INFINITY;
-        cmax = fmaxf(cmax, sv[2 * nt + e]);
-      }
-    cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 1));
-    cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 2));
-    cmax = __shfl_sync(0xffffffffu, cmax, 0);          // the g == 0 quad's maximum, warp-uniform
+    for (int off = 1; off < 32; off <<= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, off));   // warp-uniform
     const float m_new = fmaxf(m_run, cmax);
     if (m_new != -INFINITY) {                          // (warp-uniform) otherwise every key so far is masked
-      const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
-      float pe[2 * NTS], lsum = 0.f;
-#pragma unroll
-      for (int i = 0; i < 2 * NTS; i++) { pe[i] = expf(sv[i] - m_new); lsum += pe[i]; }   // exactly 0 for masked / out-of-range keys and lanes >= 4
-      lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
-      lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
-      l_run = l_run * corr + lsum;                     // meaningful on lanes 0..3
+      const float corr = att_ex2(m_run - m_new);       // ex2(-inf) = 0: nothing accumulated yet
+      const float pe0 = att_ex2(sv0 - m_new), pe1 = att_ex2(sv1 - m_new);   // exactly 0 for masked / out-of-range keys and rows >= 4
+      l_run = l_run * corr + (pe0 + pe1);
       m_run = m_new;
 #pragma unroll
       for (int j = 0; j < 8; j++) { o[j][0] *= corr; o[j][1] *= corr; }
+      const uint32_t pk = att_pack(pe0, pe1);          // probabilities rounded to bf16, like the SIMT path and torch's flash kernels
 #pragma unroll
-      for (int kp = 0; kp < KPV; kp++) {               // keys 16 kp .. 16 kp + 15: probabilities rounded to bf16 (zeros off row 0)
-        const uint32_t pa0 = att_pack(pe[4 * kp], pe[4 * kp + 1]), pa2 = att_pack(pe[4 * kp + 2], pe[4 * kp + 3]);
+      for (int kp = 0; kp < KPV; kp++) {               // keys 16 kp .. 16 kp + 15 = n-tiles 2 kp (fragment columns 0-7), 2 kp + 1 (8-15)
+        const uint32_t pa0 = (g == 2 * kp) ? pk : 0u, pa2 = (g == 2 * kp + 1) ? pk : 0u;
 #pragma unroll
         for (int jp = 0; jp < 4; jp++) {               // dims 16 jp .. 16 jp + 15: n-tiles 2 jp, 2 jp + 1
           uint32_t vb[4];
@@ -673,19 +683,19 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     }
   }
   if (prof != nullptr && lane == 0) { prof[9] = clock64(); prof[11] = n_chunks; }   // cached keys swept
-  // lanes 0..3 hold the output row: o[j][0], o[j][1] = dims 8 j + 2 t, 8 j + 2 t + 1
-  if (!p.cross && part == 0) {  // the step's own key (position `pos`), from shared memory
+  // rows 0..3 (lanes g < 4) hold partial output rows: o[j][0], o[j][1] = dims 8 j + 2 t, 8 j + 2 t + 1 over the keys of n-tile g
+  if (!p.cross && part == 0) {  // the step's own key (position `pos`), from shared memory: accounted to row 0
     float sdot = 0.f;
 #pragma unroll
     for (int e = 0; e < 2; e++) sdot = fmaf(qs[lane * 2 + e], kn[lane * 2 + e], sdot);
-    sdot = warp_sum(sdot) * p.scale;
+    sdot = warp_sum(sdot) * scale_l2;
     if (km != nullptr && pos < p.mask_len && km[pos] == 0) sdot = -INFINITY;
     const float m_new = fmaxf(m_run, sdot);
     if (m_new != -INFINITY) {
-      const float corr = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
-      const float pe = (sdot == -INFINITY) ? 0.f : expf(sdot - m_new);
-      const float pw = DT<bf16>::rnd(pe);
-      l_run = l_run * corr + pe;
+      const float corr = att_ex2(m_run - m_new);
+      const float pe = att_ex2(sdot - m_new);
+      const float pw = (g == 0) ? DT<bf16>::rnd(pe) : 0.f;
+      l_run = l_run * corr + ((lane == 0) ? pe : 0.f);
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         o[j][0] = o[j][0] * corr + pw * vn[8 * j + 2 * t];
@@ -694,6 +704,19 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
       m_run = m_new;
     }
   }
+  // add the four partial rows (lanes g = 0..3 of each t) and the 16 shares of the denominator: fixed order, once per item
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      float v = o[j][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      o[j][e] = v;
+    }
+#pragma unroll
+  for (int off = 1; off < 16; off <<= 1) l_run += __shfl_xor_sync(0xffffffffu, l_run, off);
+  l_run = __shfl_sync(0xffffffffu, l_run, 0);
   if (nparts == 2) {  // merge the two warps' partial softmax states (fixed order: part 0 then part 1)
     if (part == 1) {
       if (lane < 4) {
@@ -706,8 +729,8 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     if (part == 0) {
       const float m1 = xch[HD], l1 = xch[HD + 1];
       const float mm = fmaxf(m_run, m1);
-      const float c0 = (m_run == -INFINITY) ? 0.f : expf(m_run - mm);
-      const float c1 = (m1 == -INFINITY) ? 0.f : expf(m1 - mm);
+      const float c0 = (m_run == -INFINITY) ? 0.f : att_ex2(m_run - mm);   // (-inf) - (-inf) would be NaN
+      const float c1 = (m1 == -INFINITY) ? 0.f : att_ex2(m1 - mm);
       l_run = l_run * c0 + l1 * c1;
       if (lane < 4) {
 #pragma unroll

@@ -415,7 +415,7 @@ __device__ __forceinline__ void attn_phase(const StepParams& p, Smem& sm, const 
 // one CTA per (utterance, codebook) row (sample_core.cuh): 288 rows over 148 CTAs at Mini / batch 32
 template <int ITEMS>
 __device__ __noinline__ void sample_phase(const SampleArgs& sa, const ptts_gen_params& gp, int BK, int cur_len) {
-  for (int row = blockIdx.x; row < BK; row += gridDim.x) sample_row_cta<ITEMS>(sa, gp, nullptr, row, cur_len);
+  sample_all_rows_cta<ITEMS>(sa, gp, (int)blockIdx.x, (int)gridDim.x, BK, cur_len);
 }
 
 template <int ITEMS>
