@@ -356,7 +356,13 @@ def main():
     n_dec = args.decode_steps or cfg_steps
     L = n_dec + 1
     eng = model.decoder.engine
-    sess = eng.session(B, P_LEN, S_LEN, P_LEN + L)
+    # the fused step kernels hold one 32-row tile: a larger per-GPU batch (configs[3]) runs as consecutive 32-row shards through the
+    # same session, exactly as generate() does (modeling.py _fused_batch_limit)
+    TILE = 32
+    shards = [(b0, min(B, b0 + TILE)) for b0 in range(0, B, TILE)]
+    assert len({b1 - b0 for b0, b1 in shards}) == 1, "per-GPU batch must be <= 32 or a multiple of 32"
+    Bs = shards[0][1] - shards[0][0]
+    sess = eng.session(Bs, P_LEN, S_LEN, P_LEN + L)
     host = synthetic_inputs(B, H, seed=1 + rank, pin=True)
     enc_d, emask_d, prompt_d, pmask_d = [t.to(dev) for t in host]
     row_base = shard_row_base(world * B, rank, world, K)   # global (utterance, codebook) row of this shard: Philox substreams
@@ -368,13 +374,15 @@ def main():
             e, em, p, pm = [t.to(dev, non_blocking=True) for t in host]
         else:
             e, em, p, pm = enc_d, emask_d, prompt_d, pmask_d
-        sess.begin(L, seed=seed, **gen)
-        sess.prefill(p, pm, e, em)
-        sess.sample()
-        sess.decode_steps(n_dec - 1)
-        if from_host:
-            return sess.raw_ids[:, :L].to("cpu", non_blocking=False)
-        return None
+        outs = []
+        for b0, b1 in shards:
+            sess.begin(L, seed=seed, **dict(gen, row_base=row_base + b0 * K))
+            sess.prefill(p[b0:b1], pm[b0:b1], e[b0:b1], em[b0:b1])
+            sess.sample()
+            sess.decode_steps(n_dec - 1)
+            if from_host:
+                outs.append(sess.raw_ids[:, :L].to("cpu", non_blocking=False))
+        return outs if from_host else None
 
     def generate_pass(seed):
         """The public call: host tensors in, waveform on the host out (DAC decode inside generate())."""
@@ -423,12 +431,12 @@ def main():
         ms_e2e, _, wav = timed(generate_pass)
         assert wav.shape == (B, (L - K) * 512), wav.shape
         e2e_full = (ms_e2e, wav.numel() * wav.element_size())
-        sess = eng.session(B, P_LEN, S_LEN, P_LEN + L)  # (generate() may have re-created the session)
+        sess = eng.session(Bs, P_LEN, S_LEN, P_LEN + L)  # (generate() may have re-created the session)
 
     # decode-only timing for the roofline: the fused decode steps of one pass, T taken per step
     barrier()
     sess.begin(L, seed=7, **gen)
-    sess.prefill(prompt_d, pmask_d, enc_d, emask_d)
+    sess.prefill(prompt_d[:Bs], pmask_d[:Bs], enc_d[:Bs], emask_d[:Bs])
     sess.sample()
     sess.decode_steps(2)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -440,7 +448,7 @@ def main():
     dec_ms = e0.elapsed_time(e1)
     n_timed = n_dec - 3
     # step s (1-based count of tokens already appended) attends over T = P + s + 1 keys
-    byts = sum(algorithmic_bytes_per_step(B, K, V, P_LEN + s + 1, S_LEN, MODEL) for s in range(3, 3 + n_timed))
+    byts = sum(algorithmic_bytes_per_step(Bs, K, V, P_LEN + s + 1, S_LEN, MODEL) for s in range(3, 3 + n_timed))
     hbm_peak, peak_src = peaks()
     achieved = byts / (dec_ms * 1e-3) / 1e9
 
@@ -480,13 +488,13 @@ def main():
                    "tokens_only": tok_only}
         else:
             e2e = dict(tok_only, h2d_bytes_per_step=h2d)
-        traffic, traffic_src = ncu_step_traffic()
+        traffic, traffic_src = ncu_step_traffic() if (headline and int(fused) == 2) else (None, "no ncu capture committed for this configuration")
         line = {
             "metric": "audio codec tokens/sec (all codebooks)", "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{model_name} bf16 batch={B}/GPU {n_dec} decode steps top-k=50 (BASELINE configs[{args.config}])",
-                       "global_batch": world * B, "prompt_len": P_LEN, "desc_len": S_LEN, "parallelism": f"batch-shard x{world}",
+                       "global_batch": world * B, "prompt_len": P_LEN, "desc_len": S_LEN, "parallelism": f"batch-shard x{world}", "row_tiles_per_gpu": len(shards),
                        "l2": f"inputs larger than L2 ({2 * step_weight_params(MODEL) / 1e9:.3f} GB weights + KV streamed per step)",
                        "timed_region": "generate_begin + prefill + sampling + fused decode steps",
                        "decode_path": {2: "cluster step kernel (step2.cu)", 1: "fused step kernel (step.cu)", 0: "multi-kernel path (shape outside the fused kernels' range)"}[int(fused)]},
@@ -506,7 +514,7 @@ def main():
         if world == 1 and headline and not args.no_gpu_reference:
             try:
                 r = gpu_reference_restatement(dev, B)
-                r["decode_only_ratio"] = (B * K / (dec_ms / n_timed * 1e-3)) / r["value"]
+                r["decode_only_ratio"] = (Bs * K / (dec_ms / n_timed * 1e-3)) / r["value"]
                 line["vs_reference_gpu"] = r
             except Exception as ex:  # pragma: no cover
                 line["vs_reference_gpu"] = {"value": None, "error": repr(ex)}

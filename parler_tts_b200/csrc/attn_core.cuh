@@ -476,6 +476,19 @@ __device__ __forceinline__ float att_ex2(float x) {   // 2^x, 2 ulp; ex2(-inf) =
   return y;
 }
 
+// one K or V stage: global -> shared memory; `stream`: evict-first in L2 (the rows are read once per token; step2.cu bulk_g2s_stream)
+__device__ __forceinline__ void att_bulk_kv(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, bool stream) {
+  if (stream) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+  } else {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  }
+}
+
 constexpr int ATT_TC_CH = 32;   // keys per ring stage: one softmax / rescale chain per 32 keys (the chain, not the MMAs, bounds a stage)
 constexpr int ATT_TC_STAGE_BYTES = 2 * ATT_TC_CH * HD * 2;   // one stage: K rows then V rows (8 KB)
 
@@ -483,7 +496,7 @@ constexpr int ATT_TC_STAGE_BYTES = 2 * ATT_TC_CH * HD * 2;   // one stage: K row
 // so the cluster step kernel calls this right after its MMA loop -- a microsecond or two before the attention itself starts --
 // and passes pre_issued = true below.
 __device__ __forceinline__ void attention_tc_issue_first(const AttnArgs& p, int b, int h, int pos, unsigned char* ring0, uint64_t* bars, int lane,
-                                                         int part, int nparts) {
+                                                         int part, int nparts, bool stream = false) {
   constexpr int CH = ATT_TC_CH;
   const int n_cached = p.cross ? p.kv_len : pos;
   const int t0 = part * CH;
@@ -499,8 +512,7 @@ __device__ __forceinline__ void attention_tc_issue_first(const AttnArgs& p, int 
   if (lane < 2) {
     const bf16* src = (lane == 0 ? kc : vc) + (size_t)t0 * HD;
     bf16* dst = reinterpret_cast<bf16*>(ring0) + (lane == 0 ? 0 : CH * HD);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(att_smem_u32(dst)), "l"(src), "r"((uint32_t)(n * HD * 2)), "r"(bar) : "memory");
+    att_bulk_kv(att_smem_u32(dst), src, (uint32_t)(n * HD * 2), bar, stream);
   }
 }
 
@@ -508,7 +520,7 @@ __device__ __forceinline__ void attention_tc_issue_first(const AttnArgs& p, int 
 // fbuf: 192 floats (query, this step's key / value); bars: this warp's two mbarriers.
 __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p, int b, int h, int pos, unsigned char* ring0, unsigned char* ring1, float* fbuf,
                                                               uint64_t* bars, int lane, uint32_t& parity, int part, int nparts, float* xch, int pair_bar,
-                                                              long long* prof = nullptr, bool pre_issued = false) {
+                                                              long long* prof = nullptr, bool pre_issued = false, bool stream = false) {
   constexpr int CH = ATT_TC_CH;
   constexpr int NTS = CH / 8;     // score n-tiles per stage
   constexpr int KPV = CH / 16;    // k16 steps of P V per stage
@@ -534,8 +546,7 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     if (lane < 2) {
       const bf16* src = (lane == 0 ? kc : vc) + (size_t)t0 * HD;
       bf16* dst = reinterpret_cast<bf16*>(st ? ring1 : ring0) + (lane == 0 ? 0 : CH * HD);
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(att_smem_u32(dst)), "l"(src), "r"((uint32_t)(n * HD * 2)), "r"(bar) : "memory");
+      att_bulk_kv(att_smem_u32(dst), src, (uint32_t)(n * HD * 2), bar, stream);
     }
   };
   auto wait_stage = [&](int st) {

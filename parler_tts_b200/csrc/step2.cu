@@ -72,6 +72,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(s32(dst_smem)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
 }
+// Streamed-once data (the weights, the K/V rows: ~1.2 GB per token, ten times the L2) is requested with an evict-first policy so that
+// it does not push out what IS reused between and inside launches: this kernel's instructions (the once-per-token phases ran at
+// ~10 cycles per instruction on cold fetches), the folded-LayerNorm vectors, the activation images, the logits.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_stream(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(s32(dst_smem)), "l"(src), "r"(bytes), "r"(s32(bar)), "l"(l2_evict_first_policy()) : "memory");
+}
 // this CTA's shared memory -> a peer's shared memory (DSMEM), completion counted on the PEER's mbarrier
 __device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster_addr, const void* src_smem, uint32_t bytes, uint32_t bar_cluster_addr) {
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -283,7 +295,8 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     // in flight (it cost ~0.5 us wherever one sat behind a 64 KB weight copy).  The one generic-written corner (the attention
     // merge scratch of the q_cross phase) is covered by the fence thread 0 executes at every device-wide barrier (request_slice).
     mbar_expect_tx(&wbar[j & 1], bytes);
-    bulk_g2s(smem + HDR + (j & 1) * WB_BYTES, src, bytes, &wbar[j & 1]);
+    if (p.dbg & 256) bulk_g2s(smem + HDR + (j & 1) * WB_BYTES, src, bytes, &wbar[j & 1]);   // (A/B: default L2 policy)
+    else bulk_g2s_stream(smem + HDR + (j & 1) * WB_BYTES, src, bytes, &wbar[j & 1]);
   };
   auto prefetch_weight_job = [&](int j) {  // ONE thread: HBM -> L2, a layer ahead
     const char* src; uint32_t bytes;
@@ -570,7 +583,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       }
       att_f = reinterpret_cast<float*>(Rg + 65536) + warp * 192;   // query / new key / new value: a corner of R the exchange never uses
       att_b = row_base + (warp >> 1);
-      if (att_b < B && !(p.dbg & 16)) attention_tc_issue_first(att, att_b, head, pos, att_ring, attbars + 2 * warp, lane, warp & 1, 2);
+      if (att_b < B && !(p.dbg & 16)) attention_tc_issue_first(att, att_b, head, pos, att_ring, attbars + 2 * warp, lane, warp & 1, 2, !(p.dbg & 256));
     }
     prof_mark(prof, 15);
     mbar_wait(xbar, par_x, 2);
@@ -666,7 +679,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
           attention_decode_item_warp<bf16, ATT_CH>(att, att_b, head, pos, region, attbars + 2 * warp, lane, att_parity, warp & 1, 2, xr, (warp >> 1) + 1);
         } else {
           attention_decode_item_warp_tc(att, att_b, head, pos, att_ring, att_ring1, att_f, attbars + 2 * warp, lane, att_parity, warp & 1, 2, att_xch,
-                                        (warp >> 1) + 1, warp == 0 ? prof : nullptr, true);
+                                        (warp >> 1) + 1, warp == 0 ? prof : nullptr, true, !(p.dbg & 256));
         }
       }
       prof_mark(prof, 5);

@@ -617,6 +617,55 @@ class ParlerTTSForConditionalGeneration:
         if streamer is not None:
             streamer.end()
 
+    def _fused_batch_limit(self):
+        """Rows one fused decode-step launch covers (None: the fused kernels are not in play, the batch runs as one session)."""
+        if self.dtype != torch.bfloat16 or os.environ.get("PTTS_FUSED", "1") == "0":
+            return None
+        return 32
+
+    def _run_token_loop(self, enc_hidden, attention_mask, prompt_hidden, prompt_mask, *, gc, max_length, seed, suppress_special, row_base,
+                        streamer=None, custom=None):
+        """begin + prefill + the token loop of one session; returns the raw token matrix [B * K, generated length]."""
+        d = self.config.decoder
+        K = d.num_codebooks
+        B, S, _ = enc_hidden.shape
+        P = 0 if prompt_hidden is None else prompt_hidden.shape[1]
+        sess = self.decoder.engine.session(B, P, S, P + max_length)
+        sess.begin(max_length, do_sample=gc.do_sample, temperature=gc.temperature, top_k=gc.top_k if gc.do_sample else 0,
+                   top_p=gc.top_p, min_new_tokens=gc.min_new_tokens or 0, seed=seed, suppress_special=suppress_special,
+                   codebook_size=self.config.audio_encoder.codebook_size, row_base=row_base)
+        if streamer is not None:
+            delayed = torch.full((B * K, 1), d.bos_token_id, dtype=torch.int64)
+            streamer.put(delayed)
+        sess.prefill(prompt_hidden, prompt_mask, enc_hidden, attention_mask)
+        if custom is not None:
+            self._host_driven_loop(sess, gc, max_length, custom[0], custom[1], streamer, seed)
+        elif streamer is not None:
+            sess.sample()
+            steps_left = max_length - 2
+            # the streamer contract is one host-visible token column per step (_sample -> streamer.put(next.cpu()))
+            col = 1
+            streamer.put(sess.raw_ids[:, col].cpu())
+            while steps_left > 0 and int(sess.state[1].item()) == 1:
+                sess.decode_steps(1)
+                col += 1
+                steps_left -= 1
+                streamer.put(sess.raw_ids[:, col].cpu())
+            streamer.end()
+        else:
+            sess.sample()
+            steps_left = max_length - 2
+            # no per-step host sync: enqueue graph replays in chunks and poll the device `active` flag between chunks
+            chunk = 64
+            while steps_left > 0:
+                n = min(chunk, steps_left)
+                sess.decode_steps(n)
+                steps_left -= n
+                if steps_left > 0 and int(sess.state[1].item()) == 0:
+                    break
+        cur_len = int(sess.state[0].item())
+        return sess.raw_ids[:, :cur_len].clone()
+
     # -- generate ----------------------------------------------------------------------------------
     @torch.no_grad()
     def generate(self, inputs: Optional[torch.Tensor] = None, generation_config: Optional[GenerationConfig] = None,
@@ -678,43 +727,23 @@ class ParlerTTSForConditionalGeneration:
             raise ValueError(f"max_length must allow at least one new token, got {max_length}")
         d = self.config.decoder
         K = d.num_codebooks
-        sess = self.decoder.engine.session(B, P, S, P + max_length)
-        sess.begin(max_length, do_sample=gc.do_sample, temperature=gc.temperature, top_k=gc.top_k if gc.do_sample else 0,
-                   top_p=gc.top_p, min_new_tokens=gc.min_new_tokens or 0, seed=seed, suppress_special=suppress_special,
-                   codebook_size=self.config.audio_encoder.codebook_size, row_base=row_base)
-        if streamer is not None:
-            delayed = torch.full((B * K, 1), d.bos_token_id, dtype=torch.int64)
-            streamer.put(delayed)
-        sess.prefill(prompt_hidden, prompt_mask, enc_hidden, attention_mask)
-        if custom_loop:
-            self._host_driven_loop(sess, gc, max_length, logits_processor or [], stopping_criteria or [], streamer, seed)
-            steps_left = 0
+        run = dict(gc=gc, max_length=max_length, seed=seed, suppress_special=suppress_special)
+        limit = self._fused_batch_limit()
+        if limit is not None and B > limit and not custom_loop and streamer is None:
+            # The fused decode-step kernels hold one 32-row tile: a larger batch runs as consecutive shards of <= 32 utterances through
+            # the same session.  The result is the one the whole batch would give: the Philox draw is keyed by the global row
+            # (row_base), the processors' state is per utterance, and a finished utterance emits pad ids until the longest one ends.
+            parts = []
+            for b0 in range(0, B, limit):
+                sl = slice(b0, min(B, b0 + limit))
+                parts.append(self._run_token_loop(enc_hidden[sl], None if attention_mask is None else attention_mask[sl],
+                                                  None if prompt_hidden is None else prompt_hidden[sl],
+                                                  None if prompt_mask is None else prompt_mask[sl], row_base=row_base + b0 * K, **run))
+            n = max(t.shape[1] for t in parts)
+            output_ids = torch.cat([torch.nn.functional.pad(t, (0, n - t.shape[1]), value=d.pad_token_id) for t in parts], dim=0)
         else:
-            sess.sample()
-            steps_left = max_length - 2
-        if custom_loop:
-            pass
-        elif streamer is not None:
-            # the streamer contract is one host-visible token column per step (_sample -> streamer.put(next.cpu()))
-            col = 1
-            streamer.put(sess.raw_ids[:, col].cpu())
-            while steps_left > 0 and int(sess.state[1].item()) == 1:
-                sess.decode_steps(1)
-                col += 1
-                steps_left -= 1
-                streamer.put(sess.raw_ids[:, col].cpu())
-            streamer.end()
-        else:
-            # no per-step host sync: enqueue graph replays in chunks and poll the device `active` flag between chunks
-            chunk = 64
-            while steps_left > 0:
-                n = min(chunk, steps_left)
-                sess.decode_steps(n)
-                steps_left -= n
-                if steps_left > 0 and int(sess.state[1].item()) == 0:
-                    break
-        cur_len = int(sess.state[0].item())
-        output_ids = sess.raw_ids[:, :cur_len].clone()
+            output_ids = self._run_token_loop(enc_hidden, attention_mask, prompt_hidden, prompt_mask, row_base=row_base, streamer=streamer,
+                                              custom=(logits_processor or [], stopping_criteria or []) if custom_loop else None, **run)
 
         # apply the stashed delay mask, then keep only the free cells (:3586-3597)
         _, full_mask = build_delay_pattern_mask(output_ids[:, :1], d.bos_token_id, d.pad_token_id, max_length, K)

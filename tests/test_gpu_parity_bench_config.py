@@ -210,6 +210,59 @@ def test_sampling_is_shard_invariant():
     assert not np.array_equal(lo[:, 1:n], hi[:, 1:n])  # different utterances really draw different streams
 
 
+def test_large_layer_shape_fused_step_vs_oracle():
+    """BASELINE configs[3] layer shape (Parler-TTS-Large: H 1536, 24 heads, F 6144; helpers/model_init_scripts/init_large_model.py:25-43),
+    bf16, 32 rows, 2 layers: the fused step kernel (step.cu -- the cluster kernel's shape range ends at H 1024) teacher-forced on the
+    oracle's greedy history, logits within the bf16 bound measured at the Mini shape."""
+    cfg = mini_cfg(num_hidden_layers=2, max_position_embeddings=64, hidden_size=1536, num_attention_heads=24, ffn_dim=6144)
+    w = make_decoder_weights(cfg, seed=6, head_std=0.2)
+    dcfg = tiny_dac_cfg(n_codebooks=cfg.num_codebooks, codebook_size=1024)
+    model = build_product_model(cfg, dcfg, w, make_dac_weights(dcfg, seed=1), dtype=torch.bfloat16)
+    B, S, P, steps = 32, 12, 6, 6
+    enc, enc_mask, prompt, prompt_mask = synth_inputs(cfg, B, S, P, seed=5)
+    enc, prompt = enc.bfloat16().float(), prompt.bfloat16().float()
+    L = steps + 1
+    ref = generate_tokens(OracleDecoder(cfg, w, torch.bfloat16), cfg, enc, enc_mask, prompt, prompt_mask,
+                          dict(max_length=L, do_sample=False), collect_logits=True)
+    sess = model.decoder.engine.session(B, P, S, P + L)
+    sess.begin(L, do_sample=False)
+    sess.prefill(prompt.to(DEV), prompt_mask, enc.to(DEV), enc_mask)
+    assert sess.fused >= 1, "a fused step kernel must cover the Large layer shape at 32 rows"
+    worst = 0.0
+    for t in range(steps):
+        if t > 0:
+            sess.decode_forward()
+        a, b = sess.logits.float().cpu().numpy(), ref["logits"][t]
+        worst = max(worst, float(np.abs(a - b).max()) / float(np.abs(b).max()))
+        sess.sample(forced=torch.from_numpy(ref["raw_ids"][:, t + 1]).to(DEV))   # stay on the oracle's history
+    _note("large_shape", {"fused_kind": int(sess.fused), "max_rel_logit_err": worst, "layers": 2, "rows": B})
+    assert worst < 0.03, f"Large-shape bf16 logits differ from the oracle by {worst:.4f} of the logit scale"
+
+
+def test_generate_batch_above_one_tile_runs_as_shards(monkeypatch):
+    """generate() runs a batch larger than the fused kernels' 32-row tile as consecutive shards; the result
+    must be the one the whole batch gives (tokens, pad tail of early finishers, waveform).  fp32 makes both sides bit-exact: the
+    tile limit is forced to 2 and 3 rows on a batch of 5 (ragged last shard) and compared with the unsharded run."""
+    cfg = tiny_cfg()
+    w = make_decoder_weights(cfg, seed=45, head_std=0.5)
+    dcfg = tiny_dac_cfg()
+    model = build_product_model(cfg, dcfg, w, make_dac_weights(dcfg, seed=2), dtype=torch.float32)
+    B, S, P = 5, 6, 3
+    enc, enc_mask, prompt, prompt_mask = synth_inputs(cfg, B, S, P, seed=9, masks=True)
+    kw = dict(encoder_outputs=(enc.to(DEV),), attention_mask=enc_mask, prompt_hidden_states=prompt.to(DEV), prompt_attention_mask=prompt_mask,
+              do_sample=True, top_k=12, temperature=0.9, seed=77, max_new_tokens=24, return_codes=True)
+    assert model._fused_batch_limit() is None          # fp32: one session for the whole batch
+    audio0, out0 = model.generate(**kw)
+    for limit in (2, 3):
+        monkeypatch.setattr(model, "_fused_batch_limit", lambda limit=limit: limit)
+        audio1, out1 = model.generate(**kw)
+        assert torch.equal(out0.raw_ids, out1.raw_ids), f"shards of {limit}: token matrix differs"
+        assert torch.equal(out0.audio_codes, out1.audio_codes)
+        assert out0.audios_length == out1.audios_length
+        assert torch.equal(audio0, audio1)
+    _note("batch_shards", {"batch": B, "limits": [2, 3], "generated_columns": int(out0.raw_ids.shape[1])})
+
+
 def test_causal_lm_forward_step_operator():
     """ParlerTTSForCausalLM.forward as an HF-style loop drives it (reference :1865-1974 + prepare_inputs_for_generation :2909):
     BOS column + conditioning on the first call, then one delay-masked column per call over the returned cache; logits against

@@ -34,6 +34,8 @@ struct Res { long long total, bar, copy; int fail; };
 //       2: four counters (one per cluster rank), poll all four with one 16 B load, no acquire fence
 //       3: cluster barrier, then ONE arrival per cluster (rank 0), everyone polls, no acquire fence
 //       4: like 1 but the arrival is fence.acq_rel.gpu + relaxed red (same semantics, different instruction pair)
+//       5: like 1 without the 512 B of data stores (what the release waits for)      6: like 1 without fence.proxy.async.global
+//       7 / 8: like 1 with 2 / 4 polling loads kept in flight, staggered (a fresh sample of the counter every RT/2, RT/4)
 __global__ void __launch_bounds__(256, 1) k_bar(unsigned* ctr, uint32_t* data, const unsigned char* img, Res* res, int mode, int reps, int do_copy) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* mb = reinterpret_cast<uint64_t*>(smem);
@@ -47,13 +49,42 @@ __global__ void __launch_bounds__(256, 1) k_bar(unsigned* ctr, uint32_t* data, c
   int fail = 0;
   const long long t0 = clock64();
   for (int it = 1; it <= reps; it++) {
-    if (tid < 128) data[(size_t)blockIdx.x * 128 + tid] = (uint32_t)it;   // 512 B of output
+    if (tid < 128 && mode != 5) data[(size_t)blockIdx.x * 128 + tid] = (uint32_t)it;   // 512 B of output
     const long long b0 = clock64();
-    asm volatile("fence.proxy.async.global;" ::: "memory");
+    if (mode != 6) asm volatile("fence.proxy.async.global;" ::: "memory");
     if (mode == 3) { cluster_arrive(); cluster_wait(); } else __syncthreads();
     if (tid == 0) {
       unsigned spins = 0;
-      if (mode == 0 || mode == 1) {
+      if (mode == 7 || mode == 8) {
+        red_release_add(ctr, 1u);
+        const unsigned want = (unsigned)it * G;
+        const int N = (mode == 7) ? 2 : 4;
+        const long long gap = 1400 / N;   // ~ round trip / N
+        unsigned v0, v1 = 0, v2 = 0, v3 = 0;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v0) : "l"(ctr) : "memory");
+        long long c0 = clock64();
+        while (clock64() - c0 < gap) {}
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v1) : "l"(ctr) : "memory");
+        if (N == 4) {
+          c0 = clock64(); while (clock64() - c0 < gap) {}
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v2) : "l"(ctr) : "memory");
+          c0 = clock64(); while (clock64() - c0 < gap) {}
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v3) : "l"(ctr) : "memory");
+        }
+        while (true) {
+          if (v0 >= want) break;
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v0) : "l"(ctr) : "memory");
+          if (v1 >= want) break;
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v1) : "l"(ctr) : "memory");
+          if (N == 4) {
+            if (v2 >= want) break;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v2) : "l"(ctr) : "memory");
+            if (v3 >= want) break;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v3) : "l"(ctr) : "memory");
+          }
+          if (++spins > (1u << 22)) { fail = 1; break; }
+        }
+      } else if (mode == 0 || mode == 1 || mode == 5 || mode == 6) {
         red_release_add(ctr, 1u);
         while (ld_relaxed(ctr) < (unsigned)it * G) if (++spins > (1u << 22)) { fail = 1; break; }
       } else if (mode == 2) {
@@ -99,10 +130,11 @@ int main() {
   const int reps = 500;
   const size_t smem = 128 + 16384;
   CK(cudaFuncSetAttribute(k_bar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const char* names[5] = {"red.release + poll + acq_rel fence", "red.release + poll (no acquire fence)", "4 counters (per cluster rank), one 16 B poll",
-                          "cluster barrier + 1 arrival per cluster", "fence.acq_rel + relaxed red + poll"};
+  const char* names[9] = {"red.release + poll + acq_rel fence", "red.release + poll (no acquire fence)", "4 counters (per cluster rank), one 16 B poll",
+                          "cluster barrier + 1 arrival per cluster", "fence.acq_rel + relaxed red + poll", "red.release + poll, NO data stores", "red.release + poll, no proxy fence",
+                          "red.release + 2 staggered polls", "red.release + 4 staggered polls"};
   for (int copy = 0; copy < 2; copy++)
-    for (int mode = 0; mode < 5; mode++) {
+    for (int mode = 0; mode < 9; mode++) {
       CK(cudaMemset(ctr, 0, 256)); CK(cudaMemset(res, 0, sizeof(Res)));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(128); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
