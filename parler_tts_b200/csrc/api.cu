@@ -478,9 +478,23 @@ int ptts_decode_steps(ptts_session* s, int32_t n_steps, void* stream) {
   PTTS_REQUIRE(s && n_steps >= 0, "bad argument");
   if (!s->prefilled) return fail(PTTS_ESTATE, "ptts_decode_steps called before ptts_prefill");
   cudaStream_t st = (cudaStream_t)stream;
+  if (s->fused && s->cluster) {  // the cluster kernel loops over tokens itself: up to PTTS_STEPS_PER_LAUNCH (default 64) per launch
+    const char* env = getenv("PTTS_STEPS_PER_LAUNCH");   // (read per call: tests compare 1 against the default)
+    const int per_launch = env ? (atoi(env) < 1 ? 1 : atoi(env)) : 64;
+    for (int done = 0; done < n_steps;) {
+      const int m = (n_steps - done < per_launch) ? n_steps - done : per_launch;
+      s->sp.n_steps = m;
+      const int e = launch_decode_step_cluster(s->sp, st);
+      s->sp.n_steps = 1;
+      if (e) return e;
+      done += m;
+      s->launches += 1;
+    }
+    return PTTS_OK;
+  }
   if (s->fused) {  // one persistent kernel per token: nothing to gain from a graph
     for (int i = 0; i < n_steps; i++)
-      if (int e = s->cluster ? launch_decode_step_cluster(s->sp, st) : launch_decode_step(s->sp, s->sm_count, st)) return e;
+      if (int e = launch_decode_step(s->sp, s->sm_count, st)) return e;
     s->launches += n_steps;
     return PTTS_OK;
   }

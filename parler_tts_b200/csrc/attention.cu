@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnArgs p) {
   pdl_launch_dependents();
   pdl_wait();
   if (p.ctrl != nullptr && p.ctrl->active == 0) return;
-  attention_item<T>(p, blockIdx.y, blockIdx.x, sm, threadIdx.x, [] { __syncthreads(); });
+  const int per = (p.q_len + (int)gridDim.z - 1) / (int)gridDim.z;   // query positions per CTA (launch_attention: ~8)
+  attention_item<T>(p, blockIdx.y, blockIdx.x, sm, threadIdx.x, [] { __syncthreads(); }, (int)blockIdx.z * per, (int)(blockIdx.z + 1) * per);
 }
 
 // decode (q_len == 1): 8 items per CTA, one warp each (TMA-staged K/V ring per warp)
@@ -80,7 +81,8 @@ int launch_attention(const AttnArgs& a, int dtype, cudaStream_t st, bool pdl) {
     attr_done = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(a.nkv, a.B);
+  // one CTA per (K/V head, row, slice of ~8 query positions): a 33-position prefill was 87 us per launch with one CTA sweeping all of them
+  cfg.gridDim = dim3(a.nkv, a.B, (a.q_len + 7) / 8);
   cfg.blockDim = dim3(ATT_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;

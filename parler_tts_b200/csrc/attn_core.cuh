@@ -35,7 +35,7 @@ __device__ __forceinline__ float rope_elem(float x, float x_pair, int d, const T
 
 // sm: [64] q | [4][64] partials | [8] scratch | [kv capacity] scores.  `tid` in [0,128); sync() = barrier of the group.
 template <typename T, typename Sync>
-__device__ __forceinline__ void attention_item(const AttnArgs& p, int b, int kvh, float* sm, int tid, Sync sync) {
+__device__ __forceinline__ void attention_item(const AttnArgs& p, int b, int kvh, float* sm, int tid, Sync sync, int q_lo = 0, int q_hi = 1 << 30) {
   const T* __restrict__ rope_cos = reinterpret_cast<const T*>(p.rope_cos);
   const T* __restrict__ rope_sin = reinterpret_cast<const T*>(p.rope_sin);
   float* qs = sm;
@@ -54,7 +54,7 @@ __device__ __forceinline__ void attention_item(const AttnArgs& p, int b, int kvh
   if (!p.cross) {
     const int d = tid & 63;
     const bool is_v = tid >= 64;
-    for (int j = 0; j < p.q_len; j++) {
+    for (int j = 0; j < p.q_len && j < q_hi; j++) {   // (causal: positions >= q_hi are not read by this group)
       const size_t r = (size_t)b * p.q_len + j;
       const int pos = past + j;
       if (!is_v) {
@@ -78,7 +78,9 @@ __device__ __forceinline__ void attention_item(const AttnArgs& p, int b, int kvh
   const int kslot = warp * 4 + grp;    // 0..15
   const int* km = p.key_mask ? p.key_mask + (size_t)b * p.mask_ld : nullptr;
 
-  for (int j = 0; j < p.q_len; j++) {
+  // [q_lo, q_hi): the query positions this group sweeps (the prefill kernel cuts the positions over blockIdx.z; every group appends
+  // ALL new K/V rows itself above -- identical values, so the duplicate global writes are benign -- and reads only what it wrote)
+  for (int j = q_lo; j < p.q_len && j < q_hi; j++) {
     const size_t r = (size_t)b * p.q_len + j;
     const int pos = past + j;
     const int T_keys = p.cross ? p.kv_len : pos + 1;

@@ -32,6 +32,7 @@ struct StepParams {
   int do_sample_phase;     // 1: logits -> token inside the kernel (ptts_decode_steps); 0: stop at the logits
   int sample_items;        // ceil(V / 256): logits per thread of the one-CTA-per-row sampler
   int* progress;           // debug: last phase each CTA arrived at (printed on a barrier timeout)
+  int n_steps;             // cluster kernel: tokens one launch may run (stops early when every row is finished); 0 / 1 = one
   int dbg;                 // PTTS_DBG measurement switches, all off by default (1: no weight L2 prefetch, 2: no K/V prefetch,
                            // 4 / 8: omit the shared-memory proxy fence before the weight / tile copy -- timing experiments only)
   long long* prof;         // optional [(8L+3)][8] clock64 timestamps written by CTA 0 (debug / profiles)

@@ -30,6 +30,7 @@
 #include "ln_stats.cuh"
 #include "sample_core.cuh"
 #include "step.h"
+#include <type_traits>
 
 #include <cstdlib>
 
@@ -240,9 +241,9 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   Ctrl* ctrl = p.sa.ctrl;
   if (p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(size_t)(6 * p.L + 2) * PROF_STRIDE + 3] = clock64();
   if (ctrl->active == 0) return;  // generation finished: the rest of the enqueued steps are no-ops (uniform over the grid)
-  const int cur_len = ctrl->cur_len;
+  int cur_len = ctrl->cur_len;     // advanced locally when one launch runs several steps
   const unsigned gen = (unsigned)ctrl->launch_gen;
-  const int pos = p.P + cur_len - 1;  // cache position of the token being fed
+  int pos = p.P + cur_len - 1;  // cache position of the token being fed
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.H, F = p.F, B = p.B;
   const int rank = (int)cluster_rank();
@@ -271,11 +272,11 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   }
   attention_decode_init_warp(attbars + 2 * warp, lane);
   cluster_arrive(); cluster_wait();   // every peer's mbarriers exist before any remote complete_tx
-  cluster_arrive();                   // pre-arm: pairs with the first phase's "exchange buffers free" wait
   // HBM -> L2 prefetches a layer ahead cost more than they bring here (1097 -> 1070 us per step without them: the shared-memory
   // ring already runs two jobs = ~8 us ahead of its consumer, and every cp.async.bulk.prefetch.L2 is ~100 cycles of issue time
   // inside a phase): off by default, PTTS_DBG=1 switches them on (profiles/r02_step2_phases.md)
-  const bool pf_on = (p.dbg & 1) != 0;
+  const bool pf_on = (p.dbg & 1) != 0;   // PTTS_DBG=1: weight / folded-LN L2 prefetches on
+  const bool pf_kv = (p.dbg & 2) != 0;   // PTTS_DBG=2: next layer's K/V rows -> L2 during the out-proj phases
   const bool acq = (p.dbg & 32) != 0;   // PTTS_DBG=32: put the acquire fence back (grid_sync explains why it is not needed)
   unsigned* const bar_ctr = p.bar + (gen & 1u);
   unsigned bar_target = 0u;
@@ -324,11 +325,22 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   auto prefetch_kv_part = [&](int l, bool cross, int w) {  // warp w: item w >> 1, K (even w) or V (odd w)
     const int T = cross ? p.S : p.Tmax, n = cross ? p.S : pos;
     const int b = 16 * half + 4 * rank + (w >> 1);
-    if (!pf_on || n <= 0 || b >= B) return;
+    if (!pf_kv || n <= 0 || b >= B) return;
     const char* kc = cross ? p.cross_kv + p.cross_layer_stride * l : p.self_kv + p.self_layer_stride * l;
     const char* k = kc + ((size_t)b * p.nh + head) * T * HD * 2 + ((w & 1) ? (size_t)B * p.nh * T * HD * 2 : 0);
     l2_prefetch(k, (uint32_t)(n * HD * 2));
   };
+  // ---- one launch runs up to p.n_steps tokens (ptts_decode_steps): the ~10 us between dependent cooperative launches, the launch
+  // skew in front of the first barrier and the cold instruction fetches of the once-per-token phases are paid once per launch.
+  // Nothing below depends on the launch except the barrier counter, which simply keeps counting.
+  __shared__ int s_next_active;
+  const int n_steps = (p.do_sample_phase && p.n_steps > 1 && prof0 == nullptr) ? p.n_steps : 1;
+  int unfinished_prev = 0;   // ctrl->n_unfinished is 0 at launch and only grows inside it (one add per unfinished row and step)
+#pragma unroll 1
+  for (int it = 0; it < n_steps; it++) {
+  pos = p.P + cur_len - 1;
+  prof = prof0;
+  cluster_arrive_reuse(false);        // pre-arm: pairs with the first phase's "exchange buffers free" wait
   if (tid == 0) { issue_weight_job(0); issue_weight_job(1); }
   if (lane == 0) {
     for (int j = 2; j < JOBS_PER_LAYER; j++) prefetch_weight_job_part(j, warp);
@@ -405,6 +417,11 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     const int wsend = rowpart ? C * blk : blk;                       // bytes a warp stages (one block per destination rank)
     const int j0 = JOBS_PER_LAYER * l + (sub == 0 ? 0 : sub + 1);    // first weight job of this phase
     const int njobs = sub == 0 ? 2 : 1;
+    // fc2 (K slice of F/4, one n-tile per destination): with the (destination, K half) warp mapping four warps read the same A
+    // fragments -- 512 B of shared memory per HMMA, 262 KB per phase, and the shared-memory port (128 B/clk), not the tensor pipe,
+    // sets the 1.5 us.  Instead every warp takes ALL four n-tiles over an eighth of the K slice (A read once per CTA); the eight
+    // partial tiles are added inside the CTA (shared memory, fixed order) and ONE block per destination crosses the cluster.
+    const bool fc2_wide = (sub == PH_FC2) && q == 1 && (KT & 7) == 0 && !(p.dbg & 512);
 
     // folded-LayerNorm vectors of this phase's features: requested now, parked in shared memory after the MMA loop (a global
     // load followed at once by its shared-memory store would park the warp for an L2 round trip in front of the MMAs)
@@ -449,12 +466,15 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         if (q == 4) mma_slice<4, 2, 1, true>(acc, rst, xs, apitch, wb, KT, kt_lo, kt_hi, dgrp, lrow, lcol);
         else if (q == 2) mma_slice<2, 2, 2, true>(acc, rst, xs, apitch, wb, KT, kt_lo, kt_hi, dgrp, lrow, lcol);
         else mma_slice<1, 2, 4, true>(acc, rst, xs, apitch, wb, KT, kt_lo, kt_hi, dgrp, lrow, lcol);
+      } else if (fc2_wide) {
+        const uint4* wall = reinterpret_cast<const uint4*>(smem + HDR + (j0 & 1) * WB_BYTES) + lane;   // all four n-tiles
+        mma_slice<4, 2, 1, false>(acc, rst, xs, apitch, wall, KT, warp * (KT >> 3), (warp + 1) * (KT >> 3), 0, lrow, lcol);
       } else mma_slice<1, 2, 4, false>(acc, rst, xs, apitch, wb, KT, kt_lo, kt_hi, dgrp, lrow, lcol);
     }
     prof_mark(prof, 2);
     if (has_ln && tid < (rowpart ? Nc : 8 * q)) { cvec[tid] = cv1; cvec[256 + tid] = cv2; }   // read in the epilogue, several barriers later
     __syncthreads();  // activation slice and weight buffer(s) are dead
-    if (lane == 0) {  // asynchronous requests, one or two per warp so that no single thread holds the CTA back
+    if (lane == 0 && (pf_on || pf_kv)) {  // asynchronous requests, one or two per warp so that no single thread holds the CTA back
       for (int i = 0; i < njobs; i++) prefetch_weight_job_part(j0 + i + JOBS_PER_LAYER, warp);  // same job, next layer (or lm heads) -> L2
       if (sub == PH_QKV && warp == 2 && l + 1 < p.L) {   // next layer's folded-LN vectors: every CTA pulls a 1/grid share into L2
         const int64_t c_bytes = p.c_fc1 + (int64_t)2 * F * 4 - p.c_qkv;
@@ -473,11 +493,42 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     // (shared::cta -> shared::cluster, complete_tx on the destination's mbarrier); no CTA-wide synchronisation on the way ----
     //   feature-partitioned: warp (dgrp, kh) -> rank dgrp, slot 2 rank + kh: [stats 32 x 2][32 rows][RS]
     //   row-partitioned    : warp w -> every rank d, slot 8 rank + w:        [stats 4 x 2][4 rows][8 q]  (rows 4d..4d+3, the warp's columns)
-    const int nslots = rowpart ? V * C : V;
+    const int nslots = rowpart ? V * C : (fc2_wide ? C : V);
     unsigned char* send = Rg + ((act_bytes + 127) & ~127);
     unsigned char* recv = send + ((V * wsend + 127) & ~127);
     if (tid == 0) mbar_expect_tx(xbar, (uint32_t)(nslots * blk));
-    {
+    if (fc2_wide) {
+      // stage the warp's four partial tiles in the (dead) activation slice: [warp][destination][32 rows][8] fp32
+      float* stg = reinterpret_cast<float*>(Rg) + (size_t)warp * (C * ROWS * 8);
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float* base = stg + (size_t)j * (ROWS * 8) + (mt * 16 + g) * 8 + 2 * t4;
+          *reinterpret_cast<float2*>(base) = make_float2(acc[mt][j][0], acc[mt][j][1]);
+          *reinterpret_cast<float2*>(base + 64) = make_float2(acc[mt][j][2], acc[mt][j][3]);
+        }
+      __syncthreads();
+      prof_mark(prof, 14);
+      // warp w adds the eight tiles of destination w >> 1, rows 16 (w & 1) .. + 15 (lane: row l & 15, features 4 (l >> 4) .. + 3)
+      {
+        const int d = warp >> 1, row = 16 * (warp & 1) + (lane & 15), f0 = 4 * (lane >> 4);
+        const float* src = reinterpret_cast<const float*>(Rg) + (size_t)d * (ROWS * 8) + row * 8 + f0;
+        float4 v = *reinterpret_cast<const float4*>(src);
+#pragma unroll
+        for (int sw = 1; sw < 8; sw++) {
+          const float4 x = *reinterpret_cast<const float4*>(src + (size_t)sw * (C * ROWS * 8));
+          v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+        }
+        unsigned char* blk_d = send + (size_t)d * blk;
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(blk_d + 256) + row * RS + f0) = v;
+        asm volatile("bar.sync %0, 64;" ::"r"((warp >> 1) + 1) : "memory");   // the two warps of this destination
+        if ((warp & 1) == 0 && lane == 0) {
+          fence_proxy_async_smem();
+          bulk_s2peer(mapa(s32(recv + (size_t)rank * blk), (uint32_t)d), blk_d, (uint32_t)blk, mapa(s32(xbar), (uint32_t)d));
+        }
+      }
+    } else {
       unsigned char* mine = send + (size_t)warp * wsend;
       if (!rowpart) {
         float* bp = reinterpret_cast<float*>(mine + 256);
@@ -621,8 +672,13 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         for (int i = 0; i < q; i++) {
           const int f = f0 + 8 * i;
           float v = 0.f;
+          if (fc2_wide) {
 #pragma unroll
-          for (int sv = 0; sv < V; sv++) v += reinterpret_cast<const float*>(recv + (size_t)sv * blk + 256)[row * RS + f];
+            for (int sv = 0; sv < C; sv++) v += reinterpret_cast<const float*>(recv + (size_t)sv * blk + 256)[row * RS + f];
+          } else {
+#pragma unroll
+            for (int sv = 0; sv < V; sv++) v += reinterpret_cast<const float*>(recv + (size_t)sv * blk + 256)[row * RS + f];
+          }
           if (sub == PH_FC1) {
             v = stats[2 * row + 1] * (v - stats[2 * row] * cvec[f]) + cvec[256 + f];
             v = apply_act(DT<bf16>::rnd(v), p.act);
@@ -636,7 +692,6 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         }
       }
     } else {
-      const int qc = 8 * q;
       if (tid < 4) {  // rows 16 half + 4 rank + tid: statistics from the dgrp == 0 warp of every (source rank, K half)
         float S1 = 0.f, S2 = 0.f;
         for (int sr = 0; sr < C; sr++)
@@ -650,16 +705,21 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       }
       __syncthreads();
       bf16* qkv_s = reinterpret_cast<bf16*>(Rg + QKV_OFF);  // [4][Nc]
-      for (int idx = tid; idx < 4 * Nc; idx += THREADS) {
-        const int r4 = idx / Nc, col = idx - r4 * Nc;
-        const int dg = col / qc, cw = col - dg * qc;           // the warps with dgrp == dg hold this column
-        float v = 0.f;
+      auto gather = [&](auto qc_tag) {   // (the column count per warp is a constant of the phase: no run-time divisions)
+        constexpr int QC = decltype(qc_tag)::value, NC = 4 * QC;
+        for (int idx = tid; idx < 4 * NC; idx += THREADS) {
+          const int r4 = idx / NC, col = idx - r4 * NC;
+          const int dg = col / QC, cw = col - dg * QC;           // the warps with dgrp == dg hold this column
+          float v = 0.f;
 #pragma unroll
-        for (int sv = 0; sv < V; sv++)   // (source rank, K half) in order: warp index = 4 (sv & 1) + dg of rank sv >> 1
-          v += reinterpret_cast<const float*>(recv + (size_t)(8 * (sv >> 1) + 4 * (sv & 1) + dg) * blk + 32)[r4 * qc + cw];
-        v = stats[2 * r4 + 1] * (v - stats[2 * r4] * cvec[col]) + cvec[256 + col];
-        qkv_s[idx] = __float2bfloat16_rn(v);
-      }
+          for (int sv = 0; sv < V; sv++)   // (source rank, K half) in order: warp index = 4 (sv & 1) + dg of rank sv >> 1
+            v += reinterpret_cast<const float*>(recv + (size_t)(8 * (sv >> 1) + 4 * (sv & 1) + dg) * blk + 32)[r4 * QC + cw];
+          v = stats[2 * r4 + 1] * (v - stats[2 * r4] * cvec[col]) + cvec[256 + col];
+          qkv_s[idx] = __float2bfloat16_rn(v);
+        }
+      };
+      if (sub == PH_QKV) gather(std::integral_constant<int, 48>{}); else gather(std::integral_constant<int, 16>{});
+      static_assert(HD == 64, "q = 6 (q|k|v of a head over 4 warps) and q = 2 n-tiles per warp");
     }
     prof_mark(prof, 4);
     __syncthreads();   // this CTA's receive slots are consumed (and q|k|v complete): peers may send the next phase's partials
@@ -800,17 +860,32 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       sample_all_rows_cta<ITEMS>(p.sa, gp, cta, (int)gridDim.x, BK, cur_len);
       prof_mark(prof, pass == 0 ? 4 : 1);
     }
-    bar_target = grid_sync(bar_ctr, bar_target, n_phases + 1, []() {}, []() {});
+    // every CTA learns whether any row is still unfinished: thread 0 reads the counter the moment the barrier opens (after its
+    // acquire fence); the counter is reset only when the launch ends, so a step's count is the growth since the previous step
+    bar_target = grid_sync(bar_ctr, bar_target, n_phases + 1, [&]() {
+      const int tot = *reinterpret_cast<volatile int*>(&ctrl->n_unfinished);
+      s_next_active = (tot - unfinished_prev > 0) ? 1 : 0;
+      unfinished_prev = tot;
+    }, []() {});
     prof_mark(prof, 2);
   }
-  if (cta == 0 && tid == 0) {
-    if (p.do_sample_phase) {
-      const int n = atomicAdd(&ctrl->n_unfinished, 0);
+  bool go_on = false;
+  if (p.do_sample_phase) {
+    const int act = s_next_active;   // (written before the barrier's closing __syncthreads)
+    if (cta == 0 && tid == 0) {
       ctrl->cur_len = cur_len + 1;
-      ctrl->active = (n > 0) ? 1 : 0;
+      ctrl->active = act;
       ctrl->steps_run += 1;
-      ctrl->n_unfinished = 0;
     }
+    go_on = act != 0;
+    cur_len += 1;
+  }
+  if (!go_on) break;
+  }  // steps of this launch
+  if (cta == 0 && tid == 0) {
+    // (a CTA that is slower out of the last barrier may still read the counter: it then sees a count <= the one it expects and
+    // concludes "finished", which is what leaving the loop means anyway)
+    if (p.do_sample_phase) ctrl->n_unfinished = 0;
     ctrl->launch_gen = (int)(gen + 1u);
   }
 }

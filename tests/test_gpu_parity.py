@@ -537,7 +537,33 @@ def test_cluster_step_kernel_matches_legacy_step_kernel(monkeypatch):
     assert ids.shape[1] == L and np.isfinite(lg).all() and (ids[:, 1:] < 1024).all()
 
 
-def _free_run_cluster(cfg, w, B, S, P, L, gen):
+def test_cluster_kernel_many_steps_per_launch_equals_one_step_per_launch(monkeypatch):
+    """ptts_decode_steps(n) on the cluster kernel is ONE launch that loops over the tokens (cur_len, the unfinished count and the
+    stop decision advance on the device).  Same tokens, same final logits, same stopping column as one launch per token --
+    sampling included, and with an early finish inside a launch (EOS allowed after 6 tokens)."""
+    cfg = mini_cfg(num_hidden_layers=2, max_position_embeddings=96)
+    w = make_decoder_weights(cfg, seed=9, head_std=0.6)
+    B, S, P, L = 32, 12, 5, 40
+    runs = {}
+    for name, per_launch, gen in [("free", None, dict(do_sample=True, top_k=50, seed=5, min_new_tokens=L - 1, suppress_special=True, codebook_size=1024)),
+                                  ("eos", None, dict(do_sample=True, top_k=0, temperature=1.5, seed=11, min_new_tokens=6))]:
+        for per in ("1", "7", None):
+            if per is None:
+                monkeypatch.delenv("PTTS_STEPS_PER_LAUNCH", raising=False)
+            else:
+                monkeypatch.setenv("PTTS_STEPS_PER_LAUNCH", per)
+            runs[(name, per)] = _free_run_cluster(cfg, w, B, S, P, L, gen, extra_steps=9)
+        one = runs[(name, "1")]
+        for per in ("7", None):
+            got = runs[(name, per)]
+            assert got[0].shape == one[0].shape, f"{name}: stopping column differs ({got[0].shape} vs {one[0].shape})"
+            assert np.array_equal(got[0], one[0]), f"{name}: tokens differ with {per or 64} steps per launch"
+            assert np.array_equal(got[1], one[1]), f"{name}: last logits differ"
+        assert runs[(name, None)][2] < one[2]   # fewer launches
+    assert runs[("free", "1")][0].shape[1] == L
+
+
+def _free_run_cluster(cfg, w, B, S, P, L, gen, extra_steps=0):
     dcfg = tiny_dac_cfg(n_codebooks=cfg.num_codebooks, codebook_size=cfg.codebook_size)
     model = build_product_model(cfg, dcfg, w, make_dac_weights(dcfg, seed=1), dtype=torch.bfloat16)
     enc, enc_mask, prompt, prompt_mask = synth_inputs(cfg, B, S, P, seed=3)
@@ -546,7 +572,7 @@ def _free_run_cluster(cfg, w, B, S, P, L, gen):
     sess.prefill(prompt.to(DEV), prompt_mask, enc.to(DEV), enc_mask)
     assert sess.fused == 2
     sess.sample()
-    sess.decode_steps(L - 2)
+    sess.decode_steps(L - 2 + extra_steps)   # (steps past the end must be no-ops: every row is finished at max_length)
     torch.cuda.synchronize()
     n = int(sess.state[0].item())
     return sess.raw_ids[:, :n].cpu().numpy().copy(), sess.logits.cpu().numpy().copy(), sess.launches
