@@ -494,18 +494,39 @@ __device__ __forceinline__ void att_bulk_kv(uint32_t dst, const void* src, uint3
 constexpr int ATT_TC_CH = 32;   // keys per ring stage: one softmax / rescale chain per 32 keys (the chain, not the MMAs, bounds a stage)
 constexpr int ATT_TC_STAGE_BYTES = 2 * ATT_TC_CH * HD * 2;   // one stage: K rows then V rows (8 KB)
 
+// What the tensor-core decode attention needs to know about ONE (row, head) item -- resolved pointers instead of the generic AttnArgs,
+// so that the step kernel can build it from a handful of per-warp constants (the AttnArgs route cost ~500 instructions per phase
+// between the exchange send and its wait: profiles/r02_step2_phases.md).  K/V cache rows are HD wide (kv_t_stride = HD).
+struct TcItem {
+  const bf16* q;        // [HD] this step's query (shared or global memory)
+  const bf16* knew;     // [HD] this step's key / value (self-attention; nullptr for cross-attention)
+  const bf16* vnew;
+  bf16* kc;             // the item's K rows [capacity][HD] (swizzled, common.cuh kv_swz) and V rows
+  bf16* vc;
+  const int* km;        // key mask of the row (nullptr: none), valid for keys < mask_len
+  int mask_len;
+  int n_cached;         // cached keys to sweep (self: pos; cross: the description length)
+  int pos;              // position of this step's token (self: its K/V row index; rotary angle)
+  int cross;
+  int rope;
+  const bf16* rope_cos; // [positions][HD] tables (rope only)
+  const bf16* rope_sin;
+  float scale;
+  bf16* out;            // [HD] destination of the attention output
+};
+
 // Requests the FIRST K/V stage of an item into `ring0`.  The cached rows do not depend on the projection the same phase computes,
 // so the cluster step kernel calls this right after its MMA loop -- a microsecond or two before the attention itself starts --
 // and passes pre_issued = true below.
-__device__ __forceinline__ void attention_tc_issue_first(const AttnArgs& p, int b, int h, int pos, unsigned char* ring0, uint64_t* bars, int lane,
+__device__ __forceinline__ void attention_tc_issue_first(const TcItem& p, unsigned char* ring0, uint64_t* bars, int lane,
                                                          int part, int nparts, bool stream = false) {
   constexpr int CH = ATT_TC_CH;
-  const int n_cached = p.cross ? p.kv_len : pos;
+  const int n_cached = p.n_cached;
   const int t0 = part * CH;
   if (t0 >= n_cached) return;
   const int n = (n_cached - t0 < CH) ? (n_cached - t0) : CH;
-  const bf16* kc = reinterpret_cast<const bf16*>(p.kcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
-  const bf16* vc = reinterpret_cast<const bf16*>(p.vcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
+  const bf16* kc = p.kc;
+  const bf16* vc = p.vc;
   // (no proxy fence: the stage was last written by the async proxy and read with generic loads; see step2.cu issue_weight_job)
   __syncwarp();
   const uint32_t bar = att_smem_u32(&bars[0]);
@@ -520,7 +541,7 @@ __device__ __forceinline__ void attention_tc_issue_first(const AttnArgs& p, int 
 
 // ring0 / ring1: this warp's two K/V stages ([32][64] K | [32][64] V each, 16-byte aligned, anywhere in shared memory);
 // fbuf: 192 floats (query, this step's key / value); bars: this warp's two mbarriers.
-__device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p, int b, int h, int pos, unsigned char* ring0, unsigned char* ring1, float* fbuf,
+__device__ __forceinline__ void attention_decode_item_warp_tc(const TcItem& p, unsigned char* ring0, unsigned char* ring1, float* fbuf,
                                                               uint64_t* bars, int lane, uint32_t& parity, int part, int nparts, float* xch, int pair_bar,
                                                               long long* prof = nullptr, bool pre_issued = false, bool stream = false) {
   constexpr int CH = ATT_TC_CH;
@@ -529,12 +550,13 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
   float* qs = fbuf;               // [64] query (fp32 of the bf16 values)
   float* kn = qs + HD;            // [64] this step's key   (self only)
   float* vn = kn + HD;            // [64] this step's value (self only)
-  const bf16* __restrict__ rope_cos = reinterpret_cast<const bf16*>(p.rope_cos) + (size_t)pos * HD;
-  const bf16* __restrict__ rope_sin = reinterpret_cast<const bf16*>(p.rope_sin) + (size_t)pos * HD;
-  bf16* kc = reinterpret_cast<bf16*>(p.kcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
-  bf16* vc = reinterpret_cast<bf16*>(p.vcache) + (size_t)b * p.kv_b_stride + (size_t)h * p.kv_h_stride;
+  const int pos = p.pos;
+  const bf16* __restrict__ rope_cos = p.rope ? p.rope_cos + (size_t)pos * HD : nullptr;
+  const bf16* __restrict__ rope_sin = p.rope ? p.rope_sin + (size_t)pos * HD : nullptr;
+  bf16* kc = p.kc;
+  bf16* vc = p.vc;
   const int lo = lane, hi = lane + HD / 2;
-  const int n_cached = p.cross ? p.kv_len : pos;
+  const int n_cached = p.n_cached;
   const int n_chunks_all = (n_cached + CH - 1) / CH;
   const int n_chunks = (n_chunks_all > part) ? (n_chunks_all - part + nparts - 1) / nparts : 0;
 
@@ -557,12 +579,12 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     uint32_t ok, spins = 0;
     do {
       asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(par) : "memory");
-      if (!ok && ++spins > (1u << 16)) { if (lane == 0) printf("ptts: tc attention KV mbarrier timeout (cta %d b %d h %d stage %d cross %d n_cached %d)\n", (int)blockIdx.x, b, h, st, p.cross, n_cached); __trap(); }
+      if (!ok && ++spins > (1u << 16)) { if (lane == 0) printf("ptts: tc attention KV mbarrier timeout (cta %d warp %d stage %d cross %d n_cached %d)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), st, p.cross, n_cached); __trap(); }
     } while (!ok);
     parity ^= (1u << st);
   };
 
-  const int* km = p.key_mask ? p.key_mask + (size_t)b * p.mask_ld : nullptr;
+  const int* km = p.km;
   auto load_mask = [&](int c) -> int {   // one key per lane (CH == 32); requested one stage ahead of its use
     const int t0 = (part + nparts * c) * CH;
     return (km != nullptr && c < n_chunks && t0 + lane < p.mask_len && t0 + lane < n_cached) ? km[t0 + lane] : 1;
@@ -579,7 +601,7 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
 
   // query (+ rotary), this step's K/V row (self): to the cache and to shared memory
   {
-    const bf16* qsrc = reinterpret_cast<const bf16*>(p.q) + (size_t)b * p.ldq + p.q_col0 + (size_t)h * HD;
+    const bf16* qsrc = p.q;
     float x0 = __bfloat162float(qsrc[lo]), x1 = __bfloat162float(qsrc[hi]);
     if (p.rope) {
       const float y0 = rope_elem<bf16>(x0, x1, lo, rope_cos, rope_sin), y1 = rope_elem<bf16>(x1, x0, hi, rope_cos, rope_sin);
@@ -588,18 +610,18 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
     qs[lo] = x0; qs[hi] = x1;
   }
   if (!p.cross && part == 0) {
-    const bf16* ksrc = reinterpret_cast<const bf16*>(p.knew) + (size_t)b * p.ldkv + p.k_col0 + h * HD;
-    const bf16* vsrc = reinterpret_cast<const bf16*>(p.vnew) + (size_t)b * p.ldkv + p.v_col0 + h * HD;
+    const bf16* ksrc = p.knew;
+    const bf16* vsrc = p.vnew;
     float x0 = __bfloat162float(ksrc[lo]), x1 = __bfloat162float(ksrc[hi]);
     if (p.rope) {
       const float y0 = rope_elem<bf16>(x0, x1, lo, rope_cos, rope_sin), y1 = rope_elem<bf16>(x1, x0, hi, rope_cos, rope_sin);
       x0 = y0; x1 = y1;
     }
     const bf16 v0 = vsrc[lo], v1 = vsrc[hi];
-    kc[(size_t)pos * p.kv_t_stride + kv_swz(pos, lo)] = __float2bfloat16_rn(x0);
-    kc[(size_t)pos * p.kv_t_stride + kv_swz(pos, hi)] = __float2bfloat16_rn(x1);
-    vc[(size_t)pos * p.kv_t_stride + kv_swz(pos, lo)] = v0;
-    vc[(size_t)pos * p.kv_t_stride + kv_swz(pos, hi)] = v1;
+    kc[(size_t)pos * HD + kv_swz(pos, lo)] = __float2bfloat16_rn(x0);
+    kc[(size_t)pos * HD + kv_swz(pos, hi)] = __float2bfloat16_rn(x1);
+    vc[(size_t)pos * HD + kv_swz(pos, lo)] = v0;
+    vc[(size_t)pos * HD + kv_swz(pos, hi)] = v1;
     kn[lo] = DT<bf16>::rnd(x0); kn[hi] = DT<bf16>::rnd(x1);
     vn[lo] = __bfloat162float(v0); vn[hi] = __bfloat162float(v1);
   }
@@ -758,7 +780,7 @@ __device__ __forceinline__ void attention_decode_item_warp_tc(const AttnArgs& p,
   if (prof != nullptr && lane == 0) prof[10] = clock64();    // merged with the partner warp
   if (lane < 4 && part == 0) {
     const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;  // fully masked row -> zeros (never consumed)
-    bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)b * p.ldo + h * HD;
+    bf16* out = p.out;
 #pragma unroll
     for (int j = 0; j < 8; j++)
       *reinterpret_cast<__nv_bfloat162*>(out + 8 * j + 2 * t) = __floats2bfloat162_rn(o[j][0] * inv, o[j][1] * inv);

@@ -398,6 +398,13 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
   const int g = lane >> 2, t4 = lane & 3;
   const int n_phases = 6 * p.L;
 
+  // per-warp constants of the attention items (row 16 half + 4 rank + (warp >> 1), this cluster's head): element offsets of the item's
+  // K rows inside a layer's self / cross cache, the V planes' distance, and where its output goes in the attn image
+  const int att_row = 16 * half + 4 * rank + (warp >> 1);
+  const size_t self_item = ((size_t)att_row * p.nh + head) * p.Tmax * HD, self_vofs = (size_t)B * p.nh * p.Tmax * HD;
+  const size_t cross_item = ((size_t)att_row * p.nh + head) * p.S * HD, cross_vofs = (size_t)B * p.nh * p.S * HD;
+  bf16* const att_out = a_img + (size_t)(head >> 2) * x_slice_elems + (size_t)att_row * pitch + (head & 3) * HD;
+
 #pragma unroll 1
   for (int ph = 0; ph < n_phases; ph++) {
     const int l = ph / 6, sub = ph - 6 * l;
@@ -585,28 +592,25 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     // the head phases, the first K/V stage of this warp's attention item.  The rings live in the weight ring's idle space (the
     // phase's own weights are dead, the next jobs fill only the heads of the buffers), so they alias nothing the exchange uses.
     if (warp == 1 && lane == 0 && sub != PH_QC) for (int i = 0; i < njobs; i++) issue_weight_job(j0 + i + 2);
-    AttnArgs att{};
+    TcItem item{};
     int att_b = B;
     unsigned char* att_ring = nullptr; unsigned char* att_ring1 = nullptr; float* att_f = nullptr; float* att_xch = nullptr;
     if (rowpart) {
-      att.ctrl = nullptr; att.B = B; att.nh = p.nh; att.nkv = p.nh; att.q_len = 1;
-      att.past_from_ctrl = 0; att.past_len = pos; att.prefix = p.P;
-      att.rope = p.rope; att.rope_cos = blob + p.rope_cos; att.rope_sin = blob + p.rope_sin; att.scale = p.scale;
-      const bf16* qkv_s = reinterpret_cast<const bf16*>(Rg + QKV_OFF);
-      const int row_base = 16 * half + 4 * rank;
-      // row b = row_base + i, head: q at qkv_s[i][0..63] (k at +64, v at +128 for the self phase)
-      const bf16* qbase = qkv_s - (size_t)row_base * Nc - (size_t)head * HD;
-      att.q = qbase; att.ldq = Nc; att.q_col0 = 0;
-      att.ldo = pitch;   // attn image: row b, head h -> slice h / 4, column (h % 4) * 64
-      att.out = a_img + (size_t)(head >> 2) * x_slice_elems + (head & 3) * HD - (size_t)head * HD;
+      // row b = 16 half + 4 rank + (warp >> 1), this cluster's head: q at qkv_s[warp >> 1][0..63] (k at +64, v at +128 in the self phase)
+      const bf16* qrow = reinterpret_cast<const bf16*>(Rg + QKV_OFF) + (size_t)(warp >> 1) * Nc;
+      att_b = att_row;
+      item.q = qrow;
+      item.pos = pos; item.rope = p.rope; item.scale = p.scale;
+      item.rope_cos = reinterpret_cast<const bf16*>(blob + p.rope_cos); item.rope_sin = reinterpret_cast<const bf16*>(blob + p.rope_sin);
+      // attn image: row b, head h -> slice h / 4, column (h % 4) * 64
+      item.out = att_out;
       unsigned char* wb0 = smem + HDR;   // the two weight ring buffers
       if (sub == PH_QKV) {
-        att.knew = qbase; att.vnew = qbase; att.ldkv = Nc; att.k_col0 = HD; att.v_col0 = 2 * HD;
-        char* kc = p.self_kv + p.self_layer_stride * l;
-        att.kcache = kc; att.vcache = kc + (size_t)B * p.nh * p.Tmax * HD * 2;
-        att.kv_b_stride = (int64_t)p.nh * p.Tmax * HD; att.kv_h_stride = (int64_t)p.Tmax * HD; att.kv_t_stride = HD;
-        att.key_mask = p.prompt_mask; att.mask_len = p.P; att.mask_ld = p.P;
-        att.cross = 0; att.kv_len = 0; att.kv_capacity = p.Tmax;
+        item.knew = qrow + HD; item.vnew = qrow + 2 * HD;
+        bf16* kc = reinterpret_cast<bf16*>(p.self_kv + p.self_layer_stride * l) + self_item;
+        item.kc = kc; item.vc = kc + self_vofs;
+        item.km = p.prompt_mask ? p.prompt_mask + (size_t)att_b * p.P : nullptr; item.mask_len = p.P;
+        item.cross = 0; item.n_cached = pos;
         // out-proj's 16 KB go to the head of buffer (j0+2)&1, q_cross's 32 KB to the head of the other one.  Stage 0 of every warp
         // (requested now) sits in those buffers' tails; stage 1 (requested when the attention starts) in what the exchange has
         // released by then: the receive slots [34 KB, 58 KB) and the activation slice [0, 8 KB) of R, the gap behind the query
@@ -617,12 +621,11 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
                   : (warp == 5 ? Rg : bC + 49152 + (warp - 6) * ATT_TC_STAGE_BYTES));
         att_xch = reinterpret_cast<float*>(Rg + 59648) + (warp >> 1) * 128;
       } else {
-        att.knew = nullptr; att.vnew = nullptr;
-        char* ck = p.cross_kv + p.cross_layer_stride * l;
-        att.kcache = ck; att.vcache = ck + (size_t)B * p.nh * p.S * HD * 2;
-        att.kv_b_stride = (int64_t)p.nh * p.S * HD; att.kv_h_stride = (int64_t)p.S * HD; att.kv_t_stride = HD;
-        att.key_mask = p.enc_mask; att.mask_len = p.S; att.mask_ld = p.S;
-        att.cross = 1; att.kv_len = p.S; att.kv_capacity = p.S;
+        item.knew = nullptr; item.vnew = nullptr;
+        bf16* ck = reinterpret_cast<bf16*>(p.cross_kv + p.cross_layer_stride * l) + cross_item;
+        item.kc = ck; item.vc = ck + cross_vofs;
+        item.km = p.enc_mask ? p.enc_mask + (size_t)att_b * p.S : nullptr; item.mask_len = p.S;
+        item.cross = 1; item.n_cached = p.S;
         // this phase's own (dead) weight buffer holds stage 0 of every warp; cross out-proj's 16 KB sit at the head of the other one.
         // Stage 1 (descriptions longer than 64 positions): R behind the exchange buffers, the gap behind the query scratch, and
         // the cross out-proj buffer's tail.
@@ -633,8 +636,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         att_xch = reinterpret_cast<float*>(bD + 32768) + (warp >> 1) * 128;
       }
       att_f = reinterpret_cast<float*>(Rg + 65536) + warp * 192;   // query / new key / new value: a corner of R the exchange never uses
-      att_b = row_base + (warp >> 1);
-      if (att_b < B && !(p.dbg & 16)) attention_tc_issue_first(att, att_b, head, pos, att_ring, attbars + 2 * warp, lane, warp & 1, 2, !(p.dbg & 256));
+      if (att_b < B && !(p.dbg & 16)) attention_tc_issue_first(item, att_ring, attbars + 2 * warp, lane, warp & 1, 2, !(p.dbg & 256));
     }
     prof_mark(prof, 15);
     mbar_wait(xbar, par_x, 2);
@@ -734,11 +736,36 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     if (rowpart) {
       if (att_b < B) {
         if (p.dbg & 16) {  // A/B: the SIMT sweep (its ring layout: K/V stages then 192 floats, inside the R region)
+          AttnArgs att{};
+          att.ctrl = nullptr; att.B = B; att.nh = p.nh; att.nkv = p.nh; att.q_len = 1;
+          att.past_from_ctrl = 0; att.past_len = pos; att.prefix = p.P;
+          att.rope = p.rope; att.rope_cos = blob + p.rope_cos; att.rope_sin = blob + p.rope_sin; att.scale = p.scale;
+          const bf16* qkv_s = reinterpret_cast<const bf16*>(Rg + QKV_OFF);
+          const int row_base = 16 * half + 4 * rank;
+          const bf16* qbase = qkv_s - (size_t)row_base * Nc - (size_t)head * HD;
+          att.q = qbase; att.ldq = Nc; att.q_col0 = 0;
+          att.ldo = pitch;
+          att.out = a_img + (size_t)(head >> 2) * x_slice_elems + (head & 3) * HD - (size_t)head * HD;
+          if (sub == PH_QKV) {
+            att.knew = qbase; att.vnew = qbase; att.ldkv = Nc; att.k_col0 = HD; att.v_col0 = 2 * HD;
+            char* kc = p.self_kv + p.self_layer_stride * l;
+            att.kcache = kc; att.vcache = kc + (size_t)B * p.nh * p.Tmax * HD * 2;
+            att.kv_b_stride = (int64_t)p.nh * p.Tmax * HD; att.kv_h_stride = (int64_t)p.Tmax * HD; att.kv_t_stride = HD;
+            att.key_mask = p.prompt_mask; att.mask_len = p.P; att.mask_ld = p.P;
+            att.cross = 0; att.kv_len = 0; att.kv_capacity = p.Tmax;
+          } else {
+            att.knew = nullptr; att.vnew = nullptr;
+            char* ck = p.cross_kv + p.cross_layer_stride * l;
+            att.kcache = ck; att.vcache = ck + (size_t)B * p.nh * p.S * HD * 2;
+            att.kv_b_stride = (int64_t)p.nh * p.S * HD; att.kv_h_stride = (int64_t)p.S * HD; att.kv_t_stride = HD;
+            att.key_mask = p.enc_mask; att.mask_len = p.S; att.mask_ld = p.S;
+            att.cross = 1; att.kv_len = p.S; att.kv_capacity = p.S;
+          }
           unsigned char* region = Rg + (size_t)warp * attn_decode_smem_per_warp<bf16, ATT_CH>();
           float* xr = reinterpret_cast<float*>(Rg + 73728) + (warp >> 1) * 128;
           attention_decode_item_warp<bf16, ATT_CH>(att, att_b, head, pos, region, attbars + 2 * warp, lane, att_parity, warp & 1, 2, xr, (warp >> 1) + 1);
         } else {
-          attention_decode_item_warp_tc(att, att_b, head, pos, att_ring, att_ring1, att_f, attbars + 2 * warp, lane, att_parity, warp & 1, 2, att_xch,
+          attention_decode_item_warp_tc(item, att_ring, att_ring1, att_f, attbars + 2 * warp, lane, att_parity, warp & 1, 2, att_xch,
                                         (warp >> 1) + 1, warp == 0 ? prof : nullptr, true, !(p.dbg & 256));
         }
       }
@@ -749,6 +776,11 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       }
     }
     prof_mark(prof, 6);
+    if (p.prof != nullptr && l == p.L / 2 && tid == 0) {   // profiling runs: when does EACH CTA reach the barrier of the middle layer's phases
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      p.prof[(size_t)(n_phases + 4) * PROF_STRIDE + sub * (int)gridDim.x + cta] = (long long)ns;
+    }
 
     // ---- device-wide barrier; the next phase's activation slice is requested the moment it opens ----
     const bool last = (ph + 1 == n_phases);

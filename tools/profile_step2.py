@@ -27,7 +27,7 @@ sess.sample()
 sess.decode_steps(steps_before)
 nph = 6 * NL
 STRIDE = 16
-buf = torch.zeros((6 * NL + 4) * STRIDE, dtype=torch.int64, device=dev)
+buf = torch.zeros((6 * NL + 4) * STRIDE + 6 * 128, dtype=torch.int64, device=dev)   # + per-CTA arrival times of the middle layer's barriers
 _lib.check(_lib.lib().ptts_session_set_profile(sess.h, _lib.ptr(buf)))
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -35,7 +35,8 @@ e0.record()
 sess.decode_steps(1)
 e1.record()
 torch.cuda.synchronize()
-t = buf.cpu().view(-1, STRIDE).numpy()
+arrive = buf[(6 * NL + 4) * STRIDE:].cpu().view(6, 128).numpy().astype(np.float64)
+t = buf[:(6 * NL + 4) * STRIDE].cpu().view(-1, STRIDE).numpy()
 _lib.check(_lib.lib().ptts_session_set_profile(sess.h, None))
 us = lambda c: c / 1.965 / 1e3
 names = ["qkv+self-attn", "o-proj", "q_cross+cross-attn", "o_cross", "fc1", "fc2"]
@@ -62,6 +63,13 @@ for sub in range(6):
 print(f"per layer {tot_l:.1f} us -> {tot_l * NL:.0f} us for {NL} layers")
 span = [us(float(t[1 + 6 * l + 5][7] - t[1 + 6 * l][0])) for l in range(NL)]
 print(f"layer spans (us): first {span[0]:.1f}, second {span[1]:.1f}, mean of the rest {np.mean(span[2:]):.1f}, max {max(span[2:]):.1f}")
+if arrive.max() > 0:   # barrier arrival skew of the middle layer (globaltimer, ns): who is late?
+    for sub in range(6):
+        a = (arrive[sub] - arrive[sub].min()) / 1e3
+        order = np.argsort(a)
+        by_rank = [a[r::4].mean() for r in range(4)]
+        print(f"arrival skew {names[sub]:20s}: CTA0 {a[0]:.2f}  median {np.median(a):.2f}  p90 {np.percentile(a, 90):.2f}  max {a.max():.2f} us (CTA {order[-1]}, {order[-2]}, {order[-3]}); "
+              f"mean by cluster rank {' '.join(f'{x:.2f}' for x in by_rank)}; clusters 0-15 {a[:64].mean():.2f} / 16-31 {a[64:].mean():.2f}")
 r0, rh, rt = t[0], t[nph + 1], t[nph + 2]
 print(f"prologue {us(r0[0] - rt[3]):.2f} | embed {us(r0[6] - r0[0]):.2f} + barrier {us(r0[7] - r0[6]):.2f} | lm heads {us(rh[6] - rh[0]):.2f} "
       f"(tile + stats {us(rh[1] - rh[0]):.2f}) | barrier {us(rt[0] - rh[6]):.2f} | sampling {us(rt[1] - rt[0]):.2f} | last barrier {us(rt[2] - rt[1]):.2f} "
