@@ -6,7 +6,7 @@ K='regex:decode_step|conv_tc_kernel|final_conv|linear_|attention|embed_kernel|sa
 export PTTS_STEP_COOP=0   # Nsight Compute cannot launch a cooperative cluster grid
 export PTTS_STEPS_PER_LAUNCH=1   # one token per launch: the replays of a 64-token launch would take minutes, and `traffic` is per token
 echo "== ncu launch list (bench command, 64 decode steps)"
-timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 2600 --csv --log-file gpurun_out/launches.csv python -u bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-reference --decode-steps 64 > gpurun_out/ncu_bench.log 2>&1; wc -l gpurun_out/launches.csv
+timeout -s KILL 700 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 1300 --csv --log-file gpurun_out/launches.csv python -u bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-reference --decode-steps 64 > gpurun_out/ncu_bench.log 2>&1; wc -l gpurun_out/launches.csv
 echo "== ncu full step"
 timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:decode_step -s 40 -c 1 -o gpurun_out/step_full -f python -u bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-reference --no-dac --decode-steps 64 > gpurun_out/ncu_step.log 2>&1; tail -1 gpurun_out/ncu_step.log | cut -c1-200
 ncu -i gpurun_out/step_full.ncu-rep --page raw --csv > gpurun_out/step_full_raw.csv 2>/dev/null
