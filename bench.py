@@ -313,6 +313,40 @@ def gpu_reference_restatement(dev, B, n_steps=96):
     return out
 
 
+def streaming_measure(model, dev, batch, steps, play_steps=20):
+    """SURVEY 8f rank 1 / BASELINE configs[4] style: generate() with a ParlerTTSStreamer(incremental=True) consumer thread -- one host-visible
+    token column per step (the streamer contract), codec windows of new frames + receptive-field context.  Time to the first audio chunk and
+    real-time factor, second run (the first one creates the session and the tensor maps)."""
+    import threading
+    from parler_tts_b200 import ParlerTTSStreamer
+    enc, em, pr, pm = [t[:batch] for t in synthetic_inputs(32, MINI["hidden_size"], 1, device=dev)]
+
+    def run():
+        st = ParlerTTSStreamer(model, device=dev, play_steps=play_steps, incremental=True)
+        kw = dict(encoder_outputs=(enc,), attention_mask=em, prompt_hidden_states=pr, prompt_attention_mask=pm, do_sample=True, top_k=50,
+                  min_new_tokens=steps, max_new_tokens=steps, seed=3, _suppress_special=True, streamer=st)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        th = threading.Thread(target=lambda: model.generate(**kw))
+        th.start()
+        first, n = None, 0
+        for chunk in st:
+            m = chunk.shape[-1]
+            if m > 0 and first is None:
+                first = time.perf_counter() - t0
+            n += m
+        th.join()
+        return first, time.perf_counter() - t0, n
+
+    run()
+    first, total, n = run()
+    return {"batch": batch, "decode_steps": steps, "play_steps": play_steps, "time_to_first_audio_ms": 1e3 * first, "wall_s": total,
+            "samples_per_utterance": n, "rtf_all_utterances": batch * n / 44100 / total, "rtf_per_utterance": (n / 44100) / total,
+            "tokens_per_s": batch * MINI["num_codebooks"] * steps / total,
+            "api": "model.generate(..., streamer=ParlerTTSStreamer(model, play_steps=20, incremental=True)) consumed on a thread"}
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -511,6 +545,11 @@ def main():
         }
         if dac_info is not None:
             line["dac_decode"] = dac_info
+        if world == 1 and headline and not args.no_dac:
+            try:
+                line["streaming"] = streaming_measure(model, dev, 8, n_dec)
+            except Exception as ex:  # pragma: no cover
+                line["streaming"] = {"value": None, "error": repr(ex)}
         if world == 1 and headline and not args.no_gpu_reference:
             try:
                 r = gpu_reference_restatement(dev, B)
