@@ -19,9 +19,14 @@
 //     the same phase: QKV -> self-attention and q_cross -> cross-attention need no device-wide barrier between them.
 //     6 barriers per layer instead of 8.
 //   * weights: one contiguous slice per (phase, cluster, rank) (layout.h cpack, built once by ptts_decoder_finalize), streamed by
-//     ONE bulk copy per job into a 2 x 64 KB ring two jobs ahead and pulled HBM -> L2 a layer ahead (layer 0 of the NEXT token is
-//     prefetched during the lm-head phase: L2 survives the kernel boundary).
-//   * the activation slice of the next phase is requested by the barrier's polling thread the moment the barrier opens.
+//     ONE bulk copy per job into a 2 x 64 KB ring two jobs ahead, with an L2 evict-first policy like the K/V rows (1.2 GB per token
+//     must not evict the kernel's own instructions and the small reused tensors).  HBM -> L2 prefetches a layer ahead exist behind
+//     PTTS_DBG=1/2 and measured slower (profiles/r02_step2_phases.md).
+//   * fc2 (one n-tile per destination, K slice F/4): every warp takes all four n-tiles over an eighth of the K slice, the partial
+//     tiles are added inside the CTA and one block per destination crosses the cluster (A fragments read once per CTA).
+//   * the activation slice of the next phase is requested by the barrier's polling thread the moment the barrier opens; the
+//     per-phase cluster barrier that guards buffer reuse arrives .relaxed (its default .release is a gpu-scope MEMBAR per warp).
+//   * one launch runs up to StepParams.n_steps tokens: cur_len, the unfinished count and the stop decision advance on the device.
 // Reduction orders are fixed (k-tiles ascending inside a warp, virtual ranks 0..7 across the cluster): bit-reproducible run to
 // run.  They differ from step.cu / gemm.cu, so the two paths agree to bf16 accumulation-order noise, not bitwise.
 #include "attn_core.cuh"
@@ -101,13 +106,6 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 __device__ __forceinline__ void cluster_arrive_reuse(bool release) {
   if (release) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   else asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void st_cluster_f2(uint32_t addr, float a, float b) { asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory"); }
-__device__ __forceinline__ void st_cluster_f1(uint32_t addr, float a) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory"); }
-// arrive (release, cluster scope) on a peer's mbarrier: orders this thread's (and, through the preceding __syncwarp, its warp's)
-// remote stores before the receiver's acquire wait
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes, bool on = true) {
@@ -298,24 +296,6 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
     mbar_expect_tx(&wbar[j & 1], bytes);
     if (p.dbg & 256) bulk_g2s(smem + HDR + (j & 1) * WB_BYTES, src, bytes, &wbar[j & 1]);   // (A/B: default L2 policy)
     else bulk_g2s_stream(smem + HDR + (j & 1) * WB_BYTES, src, bytes, &wbar[j & 1]);
-  };
-  auto prefetch_weight_job = [&](int j) {  // ONE thread: HBM -> L2, a layer ahead
-    const char* src; uint32_t bytes;
-    if (pf_on && weight_job(p, j, cta, rank, src, bytes)) l2_prefetch(src, bytes);
-  };
-  // K/V rows of this rank's 4 attention items (rows 16 half + 4 rank .. + 3, head) -> L2
-  auto prefetch_kv = [&](int l, bool cross) {  // ONE thread
-    const int T = cross ? p.S : p.Tmax, n = cross ? p.S : pos;
-    if (n <= 0) return;
-    const char* kc = cross ? p.cross_kv + p.cross_layer_stride * l : p.self_kv + p.self_layer_stride * l;
-    const size_t vofs = (size_t)B * p.nh * T * HD * 2;
-    for (int i = 0; i < 4; i++) {
-      const int b = 16 * half + 4 * rank + i;
-      if (b >= B) break;
-      const char* k = kc + ((size_t)b * p.nh + head) * T * HD * 2;
-      l2_prefetch(k, (uint32_t)(n * HD * 2));
-      l2_prefetch(k + vofs, (uint32_t)(n * HD * 2));
-    }
   };
   // the same requests cut into one piece per warp (issued by lane 0 of every warp: a prefetch is ~100 cycles of issue time)
   auto prefetch_weight_job_part = [&](int j, int w) {
