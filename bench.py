@@ -519,6 +519,8 @@ def main():
             e2e = {"value": tokens / (e2e_full[0] * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": e2e_full[1],
                    "api": "model.generate(encoder_outputs=..., prompt_hidden_states=..., masks) with pinned host inputs; includes the DAC "
                           "decode; the waveform [B, samples] is read back to the host", "ms_per_step": e2e_full[0] / args.steps,
+                   "audio_seconds_per_step": world * B * (L - K) * 512 / 44100,
+                   "rtf": (world * B * (L - K) * 512 / 44100) / (e2e_full[0] / args.steps * 1e-3),   # seconds of audio per second of wall time, all utterances
                    "tokens_only": tok_only}
         else:
             e2e = dict(tok_only, h2d_bytes_per_step=h2d)
