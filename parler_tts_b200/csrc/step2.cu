@@ -517,6 +517,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
       }
     } else {
       unsigned char* mine = send + (size_t)warp * wsend;
+      const bool merged = rowpart && !(p.dbg & 1024);
       if (!rowpart) {
         float* bp = reinterpret_cast<float*>(mine + 256);
 #pragma unroll
@@ -546,11 +547,15 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
           const int row = g + 8 * hh;
-          float* bp = reinterpret_cast<float*>(mine + (size_t)(row >> 2) * blk + 32) + (row & 3) * qc + 2 * t4;
+          // block of destination rank d = row >> 2: [destination][warp] order, so that ONE copy per destination ships all eight warps'
+          // blocks (a bulk copy costs ~0.1 us of issue time through the uniform datapath: 4 per warp were 0.4 us of every warp's
+          // critical path; PTTS_DBG=1024 keeps the per-warp copies, [warp][destination] order)
+          unsigned char* blk_d = merged ? send + ((size_t)(row >> 2) * V + warp) * blk : mine + (size_t)(row >> 2) * blk;
+          float* bp = reinterpret_cast<float*>(blk_d + 32) + (row & 3) * qc + 2 * t4;
 #pragma unroll
           for (int j = 0; j < QMAX; j++)
             if (j < q) *reinterpret_cast<float2*>(bp + j * 8) = make_float2(acc[0][j][2 * hh], acc[0][j][2 * hh + 1]);
-          float* st = reinterpret_cast<float*>(mine + (size_t)(row >> 2) * blk) + (row & 3) * 2;
+          float* st = reinterpret_cast<float*>(blk_d) + (row & 3) * 2;
           if (t4 == 0) st[0] = hh ? rst.s1[0][2] : rst.s1[0][0];
           if (t4 == (g >> 1)) st[1] = hh ? ((g & 1) ? rst.sq[0][1][3] : rst.sq[0][1][2]) : ((g & 1) ? rst.sq[0][0][1] : rst.sq[0][0][0]);
         }
@@ -561,6 +566,12 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         if (lane == 0) {
           fence_proxy_async_smem();
           bulk_s2peer(mapa(s32(recv + (size_t)(2 * rank + kh) * blk), (uint32_t)dgrp), mine, (uint32_t)blk, mapa(s32(xbar), (uint32_t)dgrp));
+        }
+      } else if (merged) {
+        __syncthreads();   // all eight warps' blocks are staged
+        if (warp < C && lane == 0) {   // warp d ships [d][0..7] to rank d: it lands as slots 8 rank .. 8 rank + 7 there
+          fence_proxy_async_smem();
+          bulk_s2peer(mapa(s32(recv + (size_t)(8 * rank) * blk), (uint32_t)warp), send + (size_t)warp * V * blk, (uint32_t)(V * blk), mapa(s32(xbar), (uint32_t)warp));
         }
       } else if (lane < C) {
         fence_proxy_async_smem();
