@@ -636,15 +636,15 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
 
     // ---- epilogue: sum the partial blocks in a fixed order, LayerNorm fix-up, activation / residual ----
     if (!rowpart) {
-      if (has_ln && tid < ROWS) {
-        float S1 = 0.f, S2 = 0.f;
-        for (int v = 0; v < V; v++) { const float2 x = *reinterpret_cast<const float2*>(recv + (size_t)v * blk + tid * 8); S1 += x.x; S2 += x.y; }
-        const float mean = S1 / (float)H;
-        stats[2 * tid] = mean;
-        stats[2 * tid + 1] = rsqrtf(fmaxf(S2 / (float)H - mean * mean, 0.f) + p.eps);
-      }
-      if (has_ln) __syncthreads();
       const int row = tid >> 3, f0 = tid & 7;
+      float ln_mean = 0.f, ln_rstd = 0.f;
+      if (has_ln) {   // (fc1) every thread adds its row's eight partial statistics itself, in block order: broadcast loads instead of a
+        float S1 = 0.f, S2 = 0.f;   // 32-thread pass + CTA barrier
+#pragma unroll
+        for (int v = 0; v < V; v++) { const float2 x = *reinterpret_cast<const float2*>(recv + (size_t)v * blk + row * 8); S1 += x.x; S2 += x.y; }
+        ln_mean = S1 / (float)H;
+        ln_rstd = rsqrtf(fmaxf(S2 / (float)H - ln_mean * ln_mean, 0.f) + p.eps);
+      }
       if (row < B && sub == PH_FC1 && q == 4) {   // 4 consecutive features per thread: 8-byte loads, one 8-byte store
         const int f = 4 * f0;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -654,9 +654,8 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
           const float2 a = *reinterpret_cast<const float2*>(bp), b2 = *reinterpret_cast<const float2*>(bp + 2);
           v[0] += a.x; v[1] += a.y; v[2] += b2.x; v[3] += b2.y;
         }
-        const float mean = stats[2 * row], rstd = stats[2 * row + 1];
 #pragma unroll
-        for (int e = 0; e < 4; e++) v[e] = apply_act(DT<bf16>::rnd(rstd * (v[e] - mean * cvec[f + e]) + cvec[256 + f + e]), p.act);
+        for (int e = 0; e < 4; e++) v[e] = apply_act(DT<bf16>::rnd(ln_rstd * (v[e] - ln_mean * cvec[f + e]) + cvec[256 + f + e]), p.act);
         const int n = cta * 32 + f;
         uint2 pk;
         pk.x = att_pack(v[0], v[1]); pk.y = att_pack(v[2], v[3]);
@@ -673,7 +672,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
             for (int sv = 0; sv < V; sv++) v += reinterpret_cast<const float*>(recv + (size_t)sv * blk + 256)[row * RS + f];
           }
           if (sub == PH_FC1) {
-            v = stats[2 * row + 1] * (v - stats[2 * row] * cvec[f]) + cvec[256 + f];
+            v = ln_rstd * (v - ln_mean * cvec[f]) + cvec[256 + f];
             v = apply_act(DT<bf16>::rnd(v), p.act);
             const int n = cta * 8 * q + f;   // h feature -> slice n / KsF of the fc2 image
             h_img[(size_t)(n / KsF) * h_slice_elems + row * pitchF + (n % KsF)] = __float2bfloat16_rn(v);
@@ -685,29 +684,29 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_cluster_kernel(const _
         }
       }
     } else {
-      if (tid < 4) {  // rows 16 half + 4 rank + tid: statistics from the dgrp == 0 warp of every (source rank, K half)
-        float S1 = 0.f, S2 = 0.f;
-        for (int sr = 0; sr < C; sr++)
-          for (int k2 = 0; k2 < 2; k2++) {
-            const float2 x = *reinterpret_cast<const float2*>(recv + (size_t)(8 * sr + 4 * k2) * blk + tid * 8);
-            S1 += x.x; S2 += x.y;
-          }
-        const float mean = S1 / (float)H;
-        stats[2 * tid] = mean;
-        stats[2 * tid + 1] = rsqrtf(fmaxf(S2 / (float)H - mean * mean, 0.f) + p.eps);
-      }
-      __syncthreads();
       bf16* qkv_s = reinterpret_cast<bf16*>(Rg + QKV_OFF);  // [4][Nc]
       auto gather = [&](auto qc_tag) {   // (the column count per warp is a constant of the phase: no run-time divisions)
         constexpr int QC = decltype(qc_tag)::value, NC = 4 * QC;
         for (int idx = tid; idx < 4 * NC; idx += THREADS) {
           const int r4 = idx / NC, col = idx - r4 * NC;
           const int dg = col / QC, cw = col - dg * QC;           // the warps with dgrp == dg hold this column
+          // row 16 half + 4 rank + r4: statistics from the dgrp == 0 warp of every (source rank, K half), added by every thread itself
+          // (broadcast loads: a warp's 32 elements share the row) instead of a 4-thread pass + CTA barrier
+          float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+          for (int sr = 0; sr < C; sr++)
+#pragma unroll
+            for (int k2 = 0; k2 < 2; k2++) {
+              const float2 x = *reinterpret_cast<const float2*>(recv + (size_t)(8 * sr + 4 * k2) * blk + r4 * 8);
+              S1 += x.x; S2 += x.y;
+            }
+          const float ln_mean = S1 / (float)H;
+          const float ln_rstd = rsqrtf(fmaxf(S2 / (float)H - ln_mean * ln_mean, 0.f) + p.eps);
           float v = 0.f;
 #pragma unroll
           for (int sv = 0; sv < V; sv++)   // (source rank, K half) in order: warp index = 4 (sv & 1) + dg of rank sv >> 1
             v += reinterpret_cast<const float*>(recv + (size_t)(8 * (sv >> 1) + 4 * (sv & 1) + dg) * blk + 32)[r4 * QC + cw];
-          v = stats[2 * r4 + 1] * (v - stats[2 * r4] * cvec[col]) + cvec[256 + col];
+          v = ln_rstd * (v - ln_mean * cvec[col]) + cvec[256 + col];
           qkv_s[idx] = __float2bfloat16_rn(v);
         }
       };
